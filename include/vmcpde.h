@@ -1,0 +1,141 @@
+/* vmcpde.h -- C-ABI of libvmcpde.so: the B200 (sm_100a) implementation of vmc_pde's TDVP time-step
+ * hot path.  Plain pointers and sizes only; every `double*` below is DEVICE memory unless the comment
+ * says host; `stream` is a cudaStream_t passed as void*.  Functions return 0 on success, a nonzero
+ * code otherwise (message via vmcpde_last_error()).  No function allocates device memory behind the
+ * caller's back or synchronises the host, except where stated.
+ *
+ * The reference (RehMoritz/vmc_pde) has no FFI: its boundary is the Python surface used by main.py.
+ * Each entry point cites the reference code it replaces (paths relative to vmc_fluids/).  The Python
+ * mirror of that surface lives in vmc_pde_b200/*.py; an XLA-FFI shim over the same entry points is in
+ * vmc_pde_b200/csrc/xla_ffi_shim.cc.
+ */
+#ifndef VMCPDE_H_
+#define VMCPDE_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VMCPDE_VERSION 100
+
+/* error codes */
+#define VMCPDE_OK 0
+#define VMCPDE_EINVAL 1      /* bad argument */
+#define VMCPDE_EUNSUPPORTED 2 /* configuration not built (dimension, hidden layers, ...) */
+#define VMCPDE_ECUDA 3       /* CUDA runtime error */
+#define VMCPDE_ENUMERIC 4    /* numerical failure (non-positive Cholesky pivot, no convergence) */
+
+typedef struct vmcpde_flow vmcpde_flow; /* opaque ansatz description */
+typedef void* vmcpde_stream;
+
+/* coupling variants: class defaults of net.py:69-71 (the reference selects them by editing source) */
+enum { VMCPDE_NO_ADD = 0, VMCPDE_DIFFERENT_ADD = 1, VMCPDE_JAC_EQ_1 = 2, VMCPDE_ADD_S = 3 };
+/* latent densities: net.py:197-198 */
+enum { VMCPDE_GAUSS = 0, VMCPDE_STUDENT_T = 1 };
+/* evolution equations: evolutionEq.py:54-60 */
+enum {
+  VMCPDE_DIFFUSION = 0, VMCPDE_DIFFUSION_DRIFT = 1, VMCPDE_DIFFUSION_ANISOTROPIC = 2,
+  VMCPDE_ADVECTION_HAMILTONIAN = 3, VMCPDE_ADVECTION_PAPER = 4, VMCPDE_ADVECTION_HAMILTONIAN_WDISS = 5
+};
+
+/* net.INNwProb(inds_up, inds_down, intmediate, offset, latentSpaceName, dim), net.py:185-207 */
+typedef struct vmcpde_flow_config {
+  int32_t dim;              /* d */
+  int32_t depth;            /* number of SingleBlocks */
+  int32_t n_hidden_layers;  /* len(intmediate); this release builds 1 */
+  int32_t hidden;           /* intmediate[0] */
+  int32_t variant;          /* VMCPDE_NO_ADD ... */
+  int32_t latent;           /* VMCPDE_GAUSS | VMCPDE_STUDENT_T */
+  const int32_t* ind_up;    /* host, depth * (dim/2)       : var_state.py:116 */
+  const int32_t* ind_down;  /* host, depth * (dim - dim/2) : var_state.py:117 */
+  const double* offset;     /* host, dim : network_args["offset"] */
+} vmcpde_flow_config;
+
+/* evolutionEq.EvolutionEquation parameters, evolutionEq.py:61-77 */
+typedef struct vmcpde_equation {
+  int32_t mode;            /* VMCPDE_DIFFUSION ... */
+  double D, mu, m, omega, lam, T, gamma;
+  double t;                /* time passed to the velocity field */
+  const double* tangents;  /* device, dim*dim row-major factor A with D = A^T A; required for
+                              VMCPDE_DIFFUSION_ANISOTROPIC (evolutionEq.py:18-20), else NULL */
+} vmcpde_equation;
+
+const char* vmcpde_last_error(void);
+int vmcpde_version(void);
+/* leading dimension (in doubles) used for rows of O and for S/V: num_params rounded up to 128 */
+int32_t vmcpde_padded_params(int32_t num_params);
+
+/* ---- ansatz handle ----------------------------------------------------------------------------- */
+int vmcpde_flow_create(const vmcpde_flow_config* cfg, vmcpde_flow** out);
+void vmcpde_flow_destroy(vmcpde_flow* f);
+/* VarState.numParameters, var_state.py:27 */
+int32_t vmcpde_flow_num_params(const vmcpde_flow* f);
+/* flat layout (var_state.py:106-108): out[0..3] = offsets of L, L_diag, dist_params, mu;
+ * out[4+b] = offset of blocks_b (host array of 4+depth ints) */
+int vmcpde_flow_param_offsets(const vmcpde_flow* f, int32_t* out);
+
+/* ---- (1) sampler ------------------------------------------------------------------------------- */
+/* Replaces Sampler.__call__ exact branch (sampler.py:25-34,72-86) + VarState.sample
+ * (var_state.py:76-79) + INNwProb(evaluate=False, inv=True) (net.py:214-217).
+ * Draws global sample indices [first, first+n) of the n_total-sample stream of key (key0,key1):
+ * xi = normal(key, (1, n_total, d)) in JAX's threefry2x32 counter layout, z = mu + chol(S) xi
+ * [* sqrt(nu/chi2) for Student-t] + offset, x = INN^-1(z), logp = log p_lat(z - offset) - logJ.
+ * chi2: n chi-square(nu) variates (Student-t only; the reference draws them from NumPy's global RNG,
+ * sampler.py:32), NULL for Gauss.  z_out may be NULL. */
+int vmcpde_sample(const vmcpde_flow* f, const double* theta, uint32_t key0, uint32_t key1,
+                  int64_t first, int64_t n, int64_t n_total, const double* chi2,
+                  double* x, double* logp, double* z_out, vmcpde_stream stream);
+/* raw N(0,1) draws in the same layout: out[i] = normal(key, (count_total,))[first + i]  (tdvp.py:154) */
+int vmcpde_normal(uint32_t key0, uint32_t key1, int64_t first, int64_t n, int64_t count_total,
+                  double* out, vmcpde_stream stream);
+/* U[0,1) draws, jax.random.uniform float64 layout (tdvp.py:155) */
+int vmcpde_uniform(uint32_t key0, uint32_t key1, int64_t first, int64_t n, int64_t count_total,
+                   double* out, vmcpde_stream stream);
+
+/* ---- (2) ansatz evaluation and local terms ----------------------------------------------------- */
+/* VarState.__call__(mode="eval"), var_state.py:38-43: logp[i] = log p(x[i]) */
+int vmcpde_logp(const vmcpde_flow* f, const double* theta, const double* x, int64_t n, double* logp,
+                vmcpde_stream stream);
+/* Fused VarState.__call__(mode="eval_coordgrads") + VarState.hessian + EvolutionEquation.__call__
+ * (var_state.py:55-67, evolutionEq.py:84-119).  Per sample: logp, E_loc = d_t log p, the directional
+ * derivatives of log p (grad_x for every mode but anisotropic, where they are A grad_x), the weighted
+ * second-derivative sum entering E_loc, and the row O[i,:] = d logp/d theta in flat order.
+ * O has leading dimension ldo >= P; columns [P, ldo) are written as zeros.  Any output may be NULL. */
+int vmcpde_local_terms(const vmcpde_flow* f, const double* theta, const double* x, int64_t n,
+                       const vmcpde_equation* eq, double* eloc, double* logp, double* grad,
+                       double* lap, double* O, int64_t ldo, vmcpde_stream stream);
+/* VarState.hessian, var_state.py:66-67: H[i] = d x d Hessian of log p at x[i] (row-major, n*d*d) */
+int vmcpde_hessian(const vmcpde_flow* f, const double* theta, const double* x, int64_t n, double* H,
+                   vmcpde_stream stream);
+
+/* ---- (3) moments, centring, Gram --------------------------------------------------------------- */
+/* Local sums for mpi.global_mean / global_variance (tdvp.py:37-41, mpi_wrapper.py:129-193):
+ * sums[0..3] += sum E, sum |E|, sum E^2, sum logp ; sums[4 + p] += sum_i O[i,p] for p < ldo. */
+int vmcpde_moments1(const double* eloc, const double* logp, const double* O, int64_t n, int64_t ldo,
+                    double* sums, vmcpde_stream stream);
+/* tdvp.py:40-45 on one chunk: O[i,:] -= meanO (in place); dE[i] = E[i] - meanE; Fsum[p] += sum_i dE[i]*O[i,p];
+ * wE[i] = dE[i]^2, wLp[i] = logp[i]^2 (row weights for the SNR covariance and SExp Grams);
+ * var_sum[0] += sum_i dE[i]^2.  meanO, Fsum have ldo entries. */
+int vmcpde_center_force(double* O, int64_t n, int64_t ldo, const double* meanO, const double* eloc,
+                        const double* logp, double meanE, double* dE, double* wE, double* wLp,
+                        double* Fsum, double* var_sum, vmcpde_stream stream);
+/* Weighted Gram accumulation on FP64 tensor cores (DMMA), replacing mpi.global_covariance /
+ * _cov_helper_without_p (mpi_wrapper.py:21-25,248-274; tdvp.py:46-47,68-70):
+ * for m < n_mats:  S[m][a,b] += sum_i w[m][i] * O[i,a] * O[i,b]   for the tiles of the UPPER triangle.
+ * weights[m] == NULL means w = 1.  weights / S are HOST arrays of device pointers.  Pp = padded
+ * parameter count (multiple of 128) = row/column count and leading dimension of every S[m]; O has
+ * leading dimension ldo >= Pp with zero padding columns.  n must be a multiple of 16. */
+int vmcpde_gram(const double* O, int64_t n, int64_t ldo, int32_t Pp, int32_t n_mats,
+                const double* const* weights, double* const* S, vmcpde_stream stream);
+/* S <- scale * S on the upper triangle, mirrored to the lower; then, if shift > 1e-10,
+ * S += diag(shift * diag(S)) (tdvp.py:50-51).  S_shifted may alias S or be a second Pp x Pp buffer. */
+int vmcpde_sym_finalize(double* S, int32_t Pp, double scale, vmcpde_stream stream);
+int vmcpde_diag_shift(const double* S, double* S_shifted, int32_t Pp, int32_t P, double shift,
+                      vmcpde_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VMCPDE_H_ */

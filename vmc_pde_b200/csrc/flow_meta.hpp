@@ -1,0 +1,73 @@
+// Host-side construction of FlowMeta (offsets of the flat parameter vector in the reference's order,
+// var_state.py:106-108 over flax's string-sorted param dict) from the public config.
+#pragma once
+#include <algorithm>
+#include <string>
+#include <vector>
+#include "../../include/vmcpde.h"
+#include "flow_core.cuh"
+
+namespace vmc {
+
+inline int make_flow_meta(const vmcpde_flow_config* c, FlowMeta* m, std::string* err) {
+  auto fail = [&](int code, const char* msg) { if (err) *err = msg; return code; };
+  if (!c || !m) return fail(VMCPDE_EINVAL, "null config");
+  if (c->dim < 1 || c->dim > kMaxDim) return fail(VMCPDE_EUNSUPPORTED, "dim must be in [1,16]");
+  if (c->depth < 0 || c->depth > kMaxDepth) return fail(VMCPDE_EUNSUPPORTED, "depth must be in [0,32]");
+  if (c->depth > 0 && c->n_hidden_layers != 1)
+    return fail(VMCPDE_EUNSUPPORTED, "this build supports exactly one hidden layer per SingleTrafo");
+  if (c->depth > 0 && (c->hidden < 1 || c->hidden > kMaxHidden))
+    return fail(VMCPDE_EUNSUPPORTED, "hidden width must be in [1,256]");
+  if (c->variant < 0 || c->variant > 3) return fail(VMCPDE_EINVAL, "bad coupling variant");
+  if (c->latent < 0 || c->latent > 1) return fail(VMCPDE_EINVAL, "bad latent distribution");
+  if (c->depth > 0 && c->dim < 2) return fail(VMCPDE_EINVAL, "coupling blocks need dim >= 2");
+  const int d = c->dim, d1 = d / 2, d2 = d - d / 2;
+  *m = FlowMeta{};
+  m->d = d; m->depth = c->depth; m->h = c->depth > 0 ? c->hidden : 1; m->variant = c->variant; m->latent = c->latent;
+  int off = 0;
+  m->off_L = off; off += d * (d - 1) / 2;
+  m->off_Ldiag = off; off += d;
+  m->off_dist = off; off += (c->latent == VMCPDE_STUDENT_T) ? 1 : 0;
+  m->off_mu = off; off += d;
+  const int T1 = trafo_size(d1, d2, m->h), T2 = trafo_size(d2, d1, m->h);
+  const int per_block = (c->variant == VMCPDE_DIFFERENT_ADD ? 2 : 1) * (T1 + T2);
+  std::vector<int> order(c->depth);
+  for (int b = 0; b < c->depth; ++b) order[b] = b;
+  std::sort(order.begin(), order.end(), [](int a, int b) {
+    return ("blocks_" + std::to_string(a)) < ("blocks_" + std::to_string(b));
+  });
+  for (int b : order) { m->block_off[b] = off; off += per_block; }
+  m->P = off;
+  for (int b = 0; b < c->depth; ++b) {
+    std::vector<int> seen(d, 0);
+    for (int i = 0; i < d1; ++i) {
+      int v = c->ind_up[b * d1 + i];
+      if (v < 0 || v >= d || seen[v]++) return fail(VMCPDE_EINVAL, "ind_up/ind_down must partition range(dim)");
+      m->up[b][i] = (int8_t)v;
+    }
+    for (int i = 0; i < d2; ++i) {
+      int v = c->ind_down[b * d2 + i];
+      if (v < 0 || v >= d || seen[v]++) return fail(VMCPDE_EINVAL, "ind_up/ind_down must partition range(dim)");
+      m->down[b][i] = (int8_t)v;
+    }
+  }
+  for (int i = 0; i < d; ++i) m->offset[i] = c->offset ? c->offset[i] : 0.0;
+  return VMCPDE_OK;
+}
+
+// dispatch a callable templated on the compile-time dimension
+#define VMC_DISPATCH_DIM(dim, ...)                                   \
+  switch (dim) {                                                     \
+    case 1: { constexpr int D = 1; __VA_ARGS__; break; }             \
+    case 2: { constexpr int D = 2; __VA_ARGS__; break; }             \
+    case 3: { constexpr int D = 3; __VA_ARGS__; break; }             \
+    case 4: { constexpr int D = 4; __VA_ARGS__; break; }             \
+    case 5: { constexpr int D = 5; __VA_ARGS__; break; }             \
+    case 6: { constexpr int D = 6; __VA_ARGS__; break; }             \
+    case 8: { constexpr int D = 8; __VA_ARGS__; break; }             \
+    case 10: { constexpr int D = 10; __VA_ARGS__; break; }           \
+    case 12: { constexpr int D = 12; __VA_ARGS__; break; }           \
+    default: return VMCPDE_EUNSUPPORTED;                             \
+  }
+
+}  // namespace vmc
