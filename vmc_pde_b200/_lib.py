@@ -1,0 +1,86 @@
+"""Loader of libvmcpde.so (the C-ABI of include/vmcpde.h) via ctypes.
+
+There is no CPU fallback: if the shared library is missing or CUDA is unavailable the calls raise.
+PyTorch is used only for device memory, streams and torch.distributed plumbing.
+"""
+import ctypes as C
+import os
+
+from ._capi import FlowConfig, Equation
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvmcpde.so")
+_lib = None
+
+_vp, _i64, _i32, _u32, _dbl = C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, C.c_double
+
+# name -> (restype, argtypes): mirrors include/vmcpde.h one to one
+SIGNATURES = {
+    "vmcpde_last_error": (C.c_char_p, []),
+    "vmcpde_version": (C.c_int, []),
+    "vmcpde_padded_params": (_i32, [_i32]),
+    "vmcpde_flow_create": (C.c_int, [C.POINTER(FlowConfig), C.POINTER(_vp)]),
+    "vmcpde_flow_destroy": (None, [_vp]),
+    "vmcpde_flow_num_params": (_i32, [_vp]),
+    "vmcpde_flow_param_offsets": (C.c_int, [_vp, C.POINTER(_i32)]),
+    "vmcpde_sample": (C.c_int, [_vp, _vp, _u32, _u32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "vmcpde_normal": (C.c_int, [_u32, _u32, _i64, _i64, _i64, _vp, _vp]),
+    "vmcpde_uniform": (C.c_int, [_u32, _u32, _i64, _i64, _i64, _vp, _vp]),
+    "vmcpde_logp": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "vmcpde_local_terms": (C.c_int, [_vp, _vp, _vp, _i64, C.POINTER(Equation), _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "vmcpde_hessian": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "vmcpde_moments1": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp]),
+    "vmcpde_center_force": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _dbl, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vmcpde_gram": (C.c_int, [_vp, _i64, _i64, _i32, _i32, C.POINTER(_vp), C.POINTER(_vp), _vp]),
+    "vmcpde_sym_finalize": (C.c_int, [_vp, _i32, _dbl, _vp]),
+    "vmcpde_diag_shift": (C.c_int, [_vp, _vp, _i32, _i32, _dbl, _vp]),
+    "vmcpde_dmma_peak": (C.c_int, [C.POINTER(_dbl)]),
+}
+# filled in as later translation units land (solve / eigh / observables)
+OPTIONAL_SIGNATURES = {}
+
+
+def load():
+    """Return the loaded library, raising loudly when it cannot be used."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m vmc_pde_b200.build`. "
+                           "vmc_pde_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in {**SIGNATURES, **OPTIONAL_SIGNATURES}.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().vmcpde_last_error()
+        raise RuntimeError(f"libvmcpde error {rc}: {msg.decode() if msg else ''}")
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("vmc_pde_b200 needs a CUDA device (sm_100a); there is no CPU fallback.")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr_array(tensors):
+    arr = (C.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr

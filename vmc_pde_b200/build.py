@@ -1,0 +1,77 @@
+"""In-tree build of libvmcpde.so (sm_100a) with plain nvcc; objects are compiled in parallel.
+
+    python -m vmc_pde_b200.build [--force]
+
+The library is written next to this file so that it travels with the repository snapshot to the GPU
+box (it is git-ignored).  No CPU fallback is ever built into it.
+"""
+import concurrent.futures as cf
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
+LIB = os.path.join(HERE, "libvmcpde.so")
+DIMS = (2, 3, 4, 5, 6, 8, 10, 12)
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
+PLAIN = ["capi.cu", "gram.cu", "reduce_kernels.cu", "solve.cu", "eigh.cu", "observables.cu"]
+
+
+def _units():
+    units = []
+    for f in PLAIN:
+        if os.path.exists(os.path.join(CSRC, f)):
+            units.append((f, [], f.replace(".cu", ".o")))
+    for d in DIMS:
+        units.append(("flow_kernels_dim.cu", [f"-DVMC_DIM={d}"], f"flow_kernels_dim{d}.o"))
+    return units
+
+
+def _stamp():
+    h = hashlib.sha1()
+    for root in (CSRC, os.path.join(HERE, "..", "include")):
+        for f in sorted(os.listdir(root)):
+            if f.endswith((".cu", ".cuh", ".hpp", ".h", ".cc")):
+                h.update(f.encode())
+                h.update(open(os.path.join(root, f), "rb").read())
+    h.update(" ".join(FLAGS).encode())
+    return h.hexdigest()
+
+
+def _compile(unit):
+    src, defs, obj = unit
+    cmd = [NVCC, *FLAGS, *defs, "-c", os.path.join(CSRC, src), "-o", os.path.join(OBJ, obj)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    return obj, r.returncode, r.stdout + r.stderr
+
+
+def build(force=False, verbose=True):
+    os.makedirs(OBJ, exist_ok=True)
+    stamp_file = os.path.join(OBJ, "stamp")
+    stamp = _stamp()
+    if not force and os.path.exists(LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
+        return LIB
+    units = _units()
+    with cf.ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
+        results = list(ex.map(_compile, units))
+    for obj, rc, out in results:
+        if rc != 0:
+            raise RuntimeError(f"nvcc failed for {obj}:\n{out}")
+        if verbose and out.strip():
+            print(out, file=sys.stderr)
+    objs = [os.path.join(OBJ, u[2]) for u in units]
+    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static", "-ldl", "-lrt", "-lpthread"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    open(stamp_file, "w").write(stamp)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv))

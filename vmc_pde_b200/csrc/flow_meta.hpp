@@ -12,7 +12,7 @@ namespace vmc {
 inline int make_flow_meta(const vmcpde_flow_config* c, FlowMeta* m, std::string* err) {
   auto fail = [&](int code, const char* msg) { if (err) *err = msg; return code; };
   if (!c || !m) return fail(VMCPDE_EINVAL, "null config");
-  if (c->dim < 1 || c->dim > kMaxDim) return fail(VMCPDE_EUNSUPPORTED, "dim must be in [1,16]");
+  if (c->dim < 2 || c->dim > kMaxDim) return fail(VMCPDE_EUNSUPPORTED, "dim must be in [2,16]");
   if (c->depth < 0 || c->depth > kMaxDepth) return fail(VMCPDE_EUNSUPPORTED, "depth must be in [0,32]");
   if (c->depth > 0 && c->n_hidden_layers != 1)
     return fail(VMCPDE_EUNSUPPORTED, "this build supports exactly one hidden layer per SingleTrafo");
@@ -58,7 +58,6 @@ inline int make_flow_meta(const vmcpde_flow_config* c, FlowMeta* m, std::string*
 // dispatch a callable templated on the compile-time dimension
 #define VMC_DISPATCH_DIM(dim, ...)                                   \
   switch (dim) {                                                     \
-    case 1: { constexpr int D = 1; __VA_ARGS__; break; }             \
     case 2: { constexpr int D = 2; __VA_ARGS__; break; }             \
     case 3: { constexpr int D = 3; __VA_ARGS__; break; }             \
     case 4: { constexpr int D = 4; __VA_ARGS__; break; }             \

@@ -1,0 +1,343 @@
+// Weighted Gram build  S_m += O^T diag(w_m) O  on the FP64 tensor path (DMMA.8x8x4) of sm_100a.
+//
+// Replaces mpi_wrapper._cov_helper_without_p / global_covariance (mpi_wrapper.py:21-25,248-274) as used by
+// tdvp.py:46 (S0), :47 (SExp, weights logp^2) and the EOdata@V covariance of tdvp.py:68-70 (weights dE^2).
+//
+// Design (B200-first, not a translation of the XLA dot):
+//  * tcgen05/UMMA has no FP64 kind, so the tensor path for FP64 on Blackwell is mma.sync DMMA; the kernel
+//    is built around it: 8 consumer warps, each a 64x32 register tile (64 FP64 accumulators / thread).
+//  * O is row-major [samples][Pp] (the contraction index is the slow one).  One TMA 3-D box
+//    {16 doubles, KC samples, 8 column groups} per operand and stage lands a 128-column x KC-sample
+//    panel in shared memory as [column group][sample][16 doubles] with the 128-byte swizzle; mapping the
+//    DMMA k index to samples {0,2,4,6}/{1,3,5,7} of each 8-sample group makes every fragment load
+//    bank-conflict free without padding.  Both operands of a Gram come from the same matrix, so
+//    diagonal tiles load a single panel.
+//  * Persistent CTAs (one per SM) walk the upper-triangular tile pairs of all requested matrices,
+//    ordered so that concurrently running CTAs share column panels in L2.  A producer warp runs the
+//    TMA pipeline (mbarrier full/empty ring); consumers never touch global memory until the epilogue.
+//  * Row weights (and nothing else) are applied to the B fragment in registers, so S0, SExp and the SNR
+//    covariance read the same centred O with no N x P temporaries (the reference materialises three).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <vector>
+#include "common.cuh"
+
+namespace vmc {
+
+constexpr int kBM = 128;            // tile rows (parameters a)
+constexpr int kBN = 128;            // tile cols (parameters b)
+constexpr int kKC = 16;             // samples per pipeline stage
+constexpr int kStages = 6;
+constexpr int kConsumerWarps = 8;
+constexpr int kGramThreads = (kConsumerWarps + 4) * 32;  // 2 consumer warpgroups + 1 producer warpgroup
+constexpr int kPanelBytes = kBM * kKC * 8;  // 16 KB
+constexpr int kWBytes = kKC * 8;            // 128 B of row weights
+constexpr int kStageBytes = 2 * kPanelBytes + 1024;  // A, B, weights (padded to keep 1 KB alignment)
+constexpr int kMaxMats = 4;
+
+struct GramArgs {
+  double* S[kMaxMats];
+  const double* w[kMaxMats];
+  int n_mats;
+  int tiles;      // Pp / 128
+  int Pp;
+  long long n;    // samples
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// work item -> (matrix, tile row ti <= tile col tj); matrices innermost so the weighted variants of one
+// tile pair run side by side and share both panels in L2
+__device__ __forceinline__ void decode_item(long long item, int n_mats, int tiles, int& mat, int& ti, int& tj) {
+  mat = (int)(item % n_mats);
+  long long p = item / n_mats;
+  // row-major enumeration of the upper triangle: row ti has (tiles - ti) entries
+  int r = 0;
+  long long rem = p;
+  // closed form would need a sqrt; tiles <= 512 so a short loop is fine
+  while (rem >= (long long)(tiles - r)) { rem -= (tiles - r); ++r; }
+  ti = r;
+  tj = r + (int)rem;
+}
+
+__global__ void __launch_bounds__(kGramThreads, 1)
+gram_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ GramArgs args) {
+  // dynamic shared memory is the only shared allocation, so it starts 1 KB aligned (128B-swizzle atom)
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full = (uint64_t*)(smem + kStages * kStageBytes);
+  uint64_t* empty = full + kStages;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kConsumerWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const long long n_items = (long long)args.n_mats * args.tiles * (args.tiles + 1) / 2;
+  const int k_iters = (int)(args.n / kKC);
+
+  if (warp >= kConsumerWarps) {
+    // ===== producer warpgroup: hands its registers to the consumers; one elected lane drives TMA =====
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == kConsumerWarps && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int mat, ti, tj;
+        decode_item(item, args.n_mats, args.tiles, mat, ti, tj);
+        const bool diag = (ti == tj);
+        const double* w = args.w[mat];
+        const uint32_t bytes = kPanelBytes + (diag ? 0 : kPanelBytes) + (w ? kWBytes : 0);
+        for (int k = 0; k < k_iters; ++k) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* st = smem + stage * kStageBytes;
+          mbar_expect_tx(&full[stage], bytes);
+          tma_load_3d(st, &tmap, &full[stage], 0, k * kKC, ti * (kBM / 16));
+          if (!diag) tma_load_3d(st + kPanelBytes, &tmap, &full[stage], 0, k * kKC, tj * (kBN / 16));
+          if (w) bulk_load_1d(st + 2 * kPanelBytes, w + (long long)k * kKC, kWBytes, &full[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    return;
+  }
+
+  // ===== consumers: 2 (M) x 4 (N) warps, warp tile 64 x 32 =====
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+  const int wm = warp >> 2, wn = warp & 3;
+  const int g = lane >> 2, t = lane & 3;
+  // byte offsets inside a panel, for (k-step parity sp, m8-block parity ip):
+  // sample row r = 8*(s>>1) + sp + 2t ; column chunk = (ip*4 + g/2) ^ (r & 7)
+  uint32_t off[2][2];
+#pragma unroll
+  for (int sp = 0; sp < 2; ++sp)
+#pragma unroll
+    for (int ip = 0; ip < 2; ++ip) {
+      const int r7 = sp + 2 * t;
+      off[sp][ip] = (uint32_t)(r7 * 128 + ((((ip * 4) + (g >> 1)) ^ r7) << 4) + (g & 1) * 8);
+    }
+  const uint32_t a_cg0 = (uint32_t)(wm * 4) * (kKC * 128);  // column group base of this warp's A rows
+  const uint32_t b_cg0 = (uint32_t)(wn * 2) * (kKC * 128);
+
+  int stage = 0;
+  uint32_t phase = 0;
+  for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+    int mat, ti, tj;
+    decode_item(item, args.n_mats, args.tiles, mat, ti, tj);
+    const bool diag = (ti == tj);
+    const bool weighted = args.w[mat] != nullptr;
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+    for (int k = 0; k < k_iters; ++k) {
+      mbar_wait(&full[stage], phase);
+      const uint8_t* st = smem + stage * kStageBytes;
+      const uint8_t* pa = st + a_cg0;
+      const uint8_t* pb = st + (diag ? 0 : kPanelBytes) + b_cg0;
+      const double* ws = (const double*)(st + 2 * kPanelBytes);
+#pragma unroll
+      for (int s = 0; s < kKC / 4; ++s) {
+        const int sp = s & 1;
+        const uint32_t rbase = (uint32_t)(8 * (s >> 1)) * 128;
+        double a[8], b[4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          a[i] = *(const double*)(pa + (uint32_t)(i >> 1) * (kKC * 128) + rbase + off[sp][i & 1]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          b[j] = *(const double*)(pb + (uint32_t)(j >> 1) * (kKC * 128) + rbase + off[sp][j & 1]);
+        if (weighted) {
+          const double wv = ws[8 * (s >> 1) + sp + 2 * t];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) b[j] *= wv;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[stage]);
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
+    }
+
+    // epilogue: S[ti*128 + m][tj*128 + n] += acc   (single writer per tile and launch)
+    double* S = args.S[mat];
+    const long long row0 = (long long)ti * kBM + wm * 64 + g;
+    const long long col0 = (long long)tj * kBN + wn * 32 + 2 * t;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        double2* p = (double2*)(S + (row0 + i * 8) * args.Pp + col0 + j * 8);
+        double2 v = *p;
+        v.x += acc[i][j][0];
+        v.y += acc[i][j][1];
+        *p = v;
+      }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 3-D view of the row-major matrix X[n][ldo]: {16 doubles, n rows, Pp/16 column groups}
+int make_panel_tensor_map(CUtensorMap* map, const double* X, long long n, long long ldo, int Pp) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return set_error(VMCPDE_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {16, (cuuint64_t)n, (cuuint64_t)(Pp / 16)};
+  cuuint64_t strides[2] = {(cuuint64_t)ldo * 8, 128};
+  cuuint32_t box[3] = {16, (cuuint32_t)kKC, 8};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)X, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(VMCPDE_ECUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+  return 0;
+}
+
+static size_t gram_smem_bytes() { return (size_t)kStages * kStageBytes + 2 * kStages * sizeof(uint64_t); }
+
+// DMMA issue-rate microbenchmark: register-resident chains, no memory traffic.
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) {
+  double acc[16][2];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+  double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dmma(acc[i][0], acc[i][1], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += acc[i][0] + acc[i][1];
+  if (s == 12345.678) out[0] = s;
+}
+
+}  // namespace vmc
+
+extern "C" __attribute__((visibility("default"))) int vmcpde_gram(const double* O, int64_t n, int64_t ldo, int32_t Pp, int32_t n_mats,
+                           const double* const* weights, double* const* S, vmcpde_stream stream) {
+  using namespace vmc;
+  VMC_REQUIRE(O && S, "vmcpde_gram: null pointer");
+  VMC_REQUIRE(Pp > 0 && Pp % 128 == 0, "vmcpde_gram: Pp must be a positive multiple of 128");
+  VMC_REQUIRE(ldo >= Pp && ldo % 2 == 0, "vmcpde_gram: ldo must be even and >= Pp");
+  VMC_REQUIRE(n >= 0 && n % kKC == 0, "vmcpde_gram: n must be a multiple of 16");
+  VMC_REQUIRE(n_mats >= 1 && n_mats <= kMaxMats, "vmcpde_gram: n_mats must be in [1,4]");
+  VMC_REQUIRE(((uintptr_t)O & 15) == 0, "vmcpde_gram: O must be 16-byte aligned");
+  if (n == 0) return 0;
+  GramArgs a{};
+  for (int m = 0; m < n_mats; ++m) {
+    VMC_REQUIRE(S[m] != nullptr, "vmcpde_gram: null output matrix");
+    a.S[m] = S[m];
+    a.w[m] = weights ? weights[m] : nullptr;
+    VMC_REQUIRE(((uintptr_t)a.w[m] & 15) == 0, "vmcpde_gram: weights must be 16-byte aligned");
+  }
+  a.n_mats = n_mats; a.tiles = Pp / 128; a.Pp = Pp; a.n = n;
+  CUtensorMap map;
+  if (int rc = make_panel_tensor_map(&map, O, n, ldo, Pp)) return rc;
+  const size_t smem = gram_smem_bytes();
+  static bool attr_set = false;
+  if (!attr_set) {
+    VMC_CUDA_CHECK(cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const long long n_items = (long long)n_mats * a.tiles * (a.tiles + 1) / 2;
+  int grid = num_sms();
+  if (n_items < grid) grid = (int)n_items;
+  gram_kernel<<<grid, kGramThreads, smem, (cudaStream_t)stream>>>(map, a);
+  VMC_LAUNCH_CHECK("gram_kernel");
+  return 0;
+}
+
+// Measures the register-resident DMMA rate of the device (FP64 tensor peak used as the roofline
+// denominator of the S build).  Synchronises the device.
+extern "C" __attribute__((visibility("default"))) int vmcpde_dmma_peak(double* tflops_out) {
+  using namespace vmc;
+  double* d = nullptr;
+  VMC_CUDA_CHECK(cudaMalloc(&d, 8));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int iters = 20000, blocks = num_sms() * 4;
+  dmma_peak_kernel<<<blocks, 256>>>(d, 100);
+  double best = 0.0;
+  for (int rep = 0; rep < 3; ++rep) {
+    cudaEventRecord(e0);
+    dmma_peak_kernel<<<blocks, 256>>>(d, iters);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = (double)blocks * 8 /*warps*/ * iters * 16.0 * 512.0;
+    const double tf = flops / (ms * 1e-3) * 1e-12;
+    if (tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  VMC_LAUNCH_CHECK("dmma_peak_kernel");
+  *tflops_out = best;
+  return 0;
+}
