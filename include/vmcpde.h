@@ -106,6 +106,12 @@ int vmcpde_logp(const vmcpde_flow* f, const double* theta, const double* x, int6
 int vmcpde_local_terms(const vmcpde_flow* f, const double* theta, const double* x, int64_t n,
                        const vmcpde_equation* eq, double* eloc, double* logp, double* grad,
                        double* lap, double* O, int64_t ldo, vmcpde_stream stream);
+/* INN map alone, INN.__call__(x, inv) (net.py:168-182), as used through net.apply(params, x, evaluate=False, inv)
+ * (net.py:214-217; main.py:81-82,202): y = INN(x) or INN^-1(x); logjac = its log-Jacobian; optionally the latent
+ * log-pdf of the INPUT, log p_lat(x - offset).  logjac / latent_logpdf_of_input may be NULL. */
+int vmcpde_flow_transform(const vmcpde_flow* f, const double* theta, const double* x, int64_t n,
+                          int32_t inverse, double* y, double* logjac, double* latent_logpdf_of_input,
+                          vmcpde_stream stream);
 /* VarState.hessian, var_state.py:66-67: H[i] = d x d Hessian of log p at x[i] (row-major, n*d*d) */
 int vmcpde_hessian(const vmcpde_flow* f, const double* theta, const double* x, int64_t n, double* H,
                    vmcpde_stream stream);
@@ -134,6 +140,58 @@ int vmcpde_gram(const double* O, int64_t n, int64_t ldo, int32_t Pp, int32_t n_m
 int vmcpde_sym_finalize(double* S, int32_t Pp, double scale, vmcpde_stream stream);
 int vmcpde_diag_shift(const double* S, double* S_shifted, int32_t Pp, int32_t P, double shift,
                       vmcpde_stream stream);
+
+/* General FP64 tensor-core product on the Gram pipeline: Out[M x N] = alpha * X^T Y + beta * Out with X [K x M]
+ * (ldx) and Y [K x N] (ldy) row-major.  M, N multiples of 128, K of 16 (pad with zeros). */
+int vmcpde_gemm_tn(const double* X, int64_t ldx, const double* Y, int64_t ldy, double* Out, int64_t ldo,
+                   int32_t M, int32_t N, int64_t K, double alpha, double beta, vmcpde_stream stream);
+/* Register-resident DMMA issue rate of the device in TFLOP/s (roofline denominator of the S build).
+ * Synchronises the device. */
+int vmcpde_dmma_peak(double* tflops_out);
+
+/* ---- (4) regularised solve -------------------------------------------------------------------- */
+/* Symmetric eigendecomposition on the device, replacing np.linalg.eigh at tdvp.py:61-64.
+ * S (n x n, leading dimension ld, full symmetric) is destroyed; ev[n] ascending; VT row k = eigenvector k
+ * (n x ld; the caller zero-fills the padding).  Householder tridiagonalisation + divide & conquer +
+ * back-transformation, no host synchronisation.  n <= 25472 in this release. */
+int vmcpde_eigh_workspace_bytes(int32_t n, int32_t ld, size_t* bytes);
+int vmcpde_eigh(double* S, int32_t n, int32_t ld, double* ev, double* VT, void* workspace,
+                size_t workspace_bytes, vmcpde_stream stream);
+/* Everything after eigh in TDVP.transform_to_eigenbasis / TDVP.solve (tdvp.py:66-94): VtF = V^T F;
+ * rhoVar = diag(V^T CEO V) - VtF^2 and snr = sqrt|N VtF^2 / rhoVar| when CEO (the dE^2-weighted Gram, ld x ld,
+ * zero padded) is given; invEv = (|ev/ev_max| > 1e-14) ? 1/ev : 0; regulariser 1/(1+(svdTol/|ev/ev_max|)^6)
+ * [* 1/(1+(snrTol/snr)^6)]; update = V (invEv * reg * VtF); scalars[0] = ||S update - F|| / ||F||;
+ * scalars[1] = 1 + (update^T S0 update - 2 F^T update) / meanE2. */
+int vmcpde_solve_tail_workspace_bytes(int32_t n, int32_t ld, size_t* bytes);
+int vmcpde_solve_tail(const double* ev, const double* VT, int32_t n, int32_t ld, const double* F,
+                      const double* S, const double* S0, const double* CEO, double n_glob, double svdTol,
+                      double snrTol, int32_t useSNR, double meanE2, double* VtF, double* rhoVar, double* snr,
+                      double* invEv, double* update, double* scalars, void* workspace,
+                      size_t workspace_bytes, vmcpde_stream stream);
+/* Blocked Cholesky solve S x = F for a shifted, positive definite S (diagonalShift > 0).  S is overwritten
+ * by its lower factor.  *info (device int, zero on entry) = 1 + index of the first non-positive pivot. */
+int vmcpde_chol_solve(double* S, int32_t n, int32_t ld, const double* F, double* x, int32_t* info,
+                      vmcpde_stream stream);
+/* scalars = {||S u - F|| / ||F||, 1 + (u^T S0 u - 2 F^T u)/meanE2} for a given update (tdvp.py:93-94);
+ * work2n: 2n doubles of scratch. */
+int vmcpde_solve_scalars(const double* S, const double* S0, int32_t n, int32_t ld, const double* F,
+                         const double* update, double meanE2, double* scalars, double* work2n,
+                         vmcpde_stream stream);
+
+/* ---- (5) observables (tdvp.py:143-162) --------------------------------------------------------- */
+int vmcpde_observables_workspace_bytes(int32_t d, size_t* bytes);
+/* first[0..d) += sum x; first[d] += sum logp; first[d+1] = max(first[d+1], max E_loc) */
+int vmcpde_obs_first(const double* x, const double* logp, const double* eloc, int64_t n, int32_t d,
+                     double* first, void* ws, vmcpde_stream stream);
+/* central[0..d*d) += sum dx dx^T; then d entries each of sum dx^3, dx^4, dx^5, dx^6, dx = x - mean */
+int vmcpde_obs_central(const double* x, int64_t n, int32_t d, const double* mean, double* central,
+                       void* ws, vmcpde_stream stream);
+/* uniform points in the ball of the given radius, from normal(key) and uniform(key) of the SAME key
+ * (tdvp.py:154-155): out[i] = radius * xi_i/|xi_i| * u_i^(1/d) for global indices [first, first+n) */
+int vmcpde_ball_points(uint32_t key0, uint32_t key1, int64_t first, int64_t n, int64_t n_total, int32_t d,
+                       double radius, double* out, vmcpde_stream stream);
+/* out[0] += sum_i exp(logp[i]) */
+int vmcpde_sum_exp(const double* logp, int64_t n, double* out, void* ws, vmcpde_stream stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,241 @@
+"""Thin torch-tensor wrappers over the C-ABI (include/vmcpde.h).  Internal: the public surface is the mirror of
+the reference modules (sampler, var_state, evolutionEq, tdvp, stepper, mpi_wrapper, util).
+
+torch is used for allocation and streams only; every computation is a libvmcpde.so kernel.
+"""
+import ctypes as C
+import numpy as np
+import torch
+
+from . import _lib, _capi, global_defs
+
+f64 = torch.float64
+
+
+def _dev():
+    return global_defs.device()
+
+
+def zeros(*shape, dtype=f64):
+    return torch.zeros(*shape, dtype=dtype, device=_dev())
+
+
+def empty(*shape, dtype=f64):
+    return torch.empty(*shape, dtype=dtype, device=_dev())
+
+
+def as_dev(x):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=_dev(), dtype=f64).contiguous()
+    return torch.as_tensor(np.asarray(x, dtype=np.float64), device=_dev()).contiguous()
+
+
+def round_up(n, m):
+    return (n + m - 1) // m * m
+
+
+class FlowHandle:
+    """Owns a vmcpde_flow (net.INNwProb architecture + index splits + offset)."""
+
+    def __init__(self, dim, depth, hidden, variant, latent, inds_up, inds_down, offset):
+        _lib.require_cuda()
+        self.L = _lib.load()
+        self.dim, self.depth, self.hidden = int(dim), int(depth), tuple(int(h) for h in hidden)
+        self.variant, self.latent = variant, latent
+        cfg, self._keep = _capi.make_flow_config(self.dim, self.depth, self.hidden, variant, latent, inds_up, inds_down,
+                                                 np.asarray(offset, dtype=np.float64))
+        h = C.c_void_p()
+        _lib.check(self.L.vmcpde_flow_create(C.byref(cfg), C.byref(h)))
+        self.h = h
+        self.P = int(self.L.vmcpde_flow_num_params(h))
+        self.Pp = int(self.L.vmcpde_padded_params(self.P))
+        off = (C.c_int32 * (4 + self.depth))()
+        _lib.check(self.L.vmcpde_flow_param_offsets(h, off))
+        self.offsets = list(off)
+
+    def __del__(self):
+        try:
+            self.L.vmcpde_flow_destroy(self.h)
+        except Exception:
+            pass
+
+
+def sample(flow, theta, key, first, n, n_total, chi2=None, want_z=False):
+    """vmcpde_sample: global sample indices [first, first+n) of the n_total stream of `key`."""
+    L = flow.L
+    x = empty(n, flow.dim)
+    logp = empty(n)
+    z = empty(n, flow.dim) if want_z else None
+    _lib.check(L.vmcpde_sample(flow.h, _lib.ptr(theta), int(key[0]), int(key[1]), int(first), int(n), int(n_total),
+                               _lib.ptr(chi2), _lib.ptr(x), _lib.ptr(logp), _lib.ptr(z), _lib.stream()))
+    return (x, logp, z) if want_z else (x, logp)
+
+
+def normal(key, first, n, total):
+    out = empty(n)
+    _lib.check(_lib.load().vmcpde_normal(int(key[0]), int(key[1]), int(first), int(n), int(total), _lib.ptr(out), _lib.stream()))
+    return out
+
+
+def uniform(key, first, n, total):
+    out = empty(n)
+    _lib.check(_lib.load().vmcpde_uniform(int(key[0]), int(key[1]), int(first), int(n), int(total), _lib.ptr(out), _lib.stream()))
+    return out
+
+
+def logp(flow, theta, x):
+    x = x.contiguous()
+    n = x.shape[0]
+    out = empty(n)
+    _lib.check(flow.L.vmcpde_logp(flow.h, _lib.ptr(theta), _lib.ptr(x), n, _lib.ptr(out), _lib.stream()))
+    return out
+
+
+def transform(flow, theta, x, inverse, want_latent=False):
+    x = x.contiguous()
+    n = x.shape[0]
+    y, lj = empty(n, flow.dim), empty(n)
+    lat = empty(n) if want_latent else None
+    _lib.check(flow.L.vmcpde_flow_transform(flow.h, _lib.ptr(theta), _lib.ptr(x), n, int(bool(inverse)), _lib.ptr(y),
+                                            _lib.ptr(lj), _lib.ptr(lat), _lib.stream()))
+    return y, lj, lat
+
+
+def hessian(flow, theta, x):
+    x = x.contiguous()
+    n = x.shape[0]
+    H = empty(n, flow.dim, flow.dim)
+    _lib.check(flow.L.vmcpde_hessian(flow.h, _lib.ptr(theta), _lib.ptr(x), n, _lib.ptr(H), _lib.stream()))
+    return H
+
+
+def local_terms(flow, theta, x, eq, O=None, ldo=0, want=("eloc", "logp", "grad", "lap")):
+    """Fused local terms.  eq: _capi.Equation.  O: preallocated [rows >= n, ldo] buffer or None."""
+    x = x.contiguous()
+    n = x.shape[0]
+    out = {k: None for k in ("eloc", "logp", "grad", "lap")}
+    if "eloc" in want: out["eloc"] = empty(n)
+    if "logp" in want: out["logp"] = empty(n)
+    if "grad" in want: out["grad"] = empty(n, flow.dim)
+    if "lap" in want: out["lap"] = empty(n)
+    _lib.check(flow.L.vmcpde_local_terms(flow.h, _lib.ptr(theta), _lib.ptr(x), n, C.byref(eq), _lib.ptr(out["eloc"]),
+                                         _lib.ptr(out["logp"]), _lib.ptr(out["grad"]), _lib.ptr(out["lap"]), _lib.ptr(O),
+                                         int(ldo), _lib.stream()))
+    return out
+
+
+def moments1(eloc, logp_, O, n, ldo, sums):
+    _lib.check(_lib.load().vmcpde_moments1(_lib.ptr(eloc), _lib.ptr(logp_), _lib.ptr(O), int(n), int(ldo), _lib.ptr(sums), _lib.stream()))
+
+
+def center_force(O, n, ldo, meanO, eloc, logp_, meanE, dE, wE, wLp, Fsum, var_sum):
+    _lib.check(_lib.load().vmcpde_center_force(_lib.ptr(O), int(n), int(ldo), _lib.ptr(meanO), _lib.ptr(eloc), _lib.ptr(logp_),
+                                               float(meanE), _lib.ptr(dE), _lib.ptr(wE), _lib.ptr(wLp), _lib.ptr(Fsum),
+                                               _lib.ptr(var_sum), _lib.stream()))
+
+
+def gram(O, n, ldo, Pp, weights, mats):
+    """mats[m] += sum_i weights[m][i] O[i]^T O[i] on the upper-triangular tiles; n multiple of 16."""
+    _lib.check(_lib.load().vmcpde_gram(_lib.ptr(O), int(n), int(ldo), int(Pp), len(mats), _lib.ptr_array(weights),
+                                       _lib.ptr_array(mats), _lib.stream()))
+
+
+def sym_finalize(S, Pp, scale):
+    _lib.check(_lib.load().vmcpde_sym_finalize(_lib.ptr(S), int(Pp), float(scale), _lib.stream()))
+
+
+def diag_shift(S, out, Pp, P, shift):
+    _lib.check(_lib.load().vmcpde_diag_shift(_lib.ptr(S), _lib.ptr(out), int(Pp), int(P), float(shift), _lib.stream()))
+
+
+def gram_plain(X):
+    """Full symmetric X^T X for an [n, P] tensor (pads to the kernel's tile sizes)."""
+    L = _lib.load()
+    X = X.to(f64)
+    n, P = X.shape
+    Pp = int(L.vmcpde_padded_params(P))
+    n16 = round_up(max(n, 1), 16)
+    Xp = zeros(n16, Pp)
+    Xp[:n, :P] = X
+    S = zeros(Pp, Pp)
+    gram(Xp, n16, Pp, Pp, [None], [S])
+    sym_finalize(S, Pp, 1.0)
+    return S[:P, :P].contiguous()
+
+
+_ws_cache = {}
+
+
+def workspace(nbytes):
+    """Grow-only scratch buffer shared by eigh / solve_tail."""
+    dev = _dev()
+    cur = _ws_cache.get(dev)
+    if cur is None or cur.numel() < nbytes:
+        _ws_cache[dev] = None
+        cur = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+        _ws_cache[dev] = cur
+    return cur
+
+
+def eigh_workspace_bytes(n, ld):
+    L = _lib.load()
+    a, b = C.c_size_t(0), C.c_size_t(0)
+    _lib.check(L.vmcpde_eigh_workspace_bytes(int(n), int(ld), C.byref(a)))
+    _lib.check(L.vmcpde_solve_tail_workspace_bytes(int(n), int(ld), C.byref(b)))
+    return max(a.value, b.value)
+
+
+def eigh(A_destroyed, n, ld, ev, VT, ws):
+    _lib.check(_lib.load().vmcpde_eigh(_lib.ptr(A_destroyed), int(n), int(ld), _lib.ptr(ev), _lib.ptr(VT), _lib.ptr(ws),
+                                       ws.numel(), _lib.stream()))
+
+
+def solve_tail(ev, VT, n, ld, F, S, S0, CEO, n_glob, svdTol, snrTol, useSNR, meanE2, VtF, rhoVar, snr, invEv, update,
+               scalars, ws):
+    _lib.check(_lib.load().vmcpde_solve_tail(_lib.ptr(ev), _lib.ptr(VT), int(n), int(ld), _lib.ptr(F), _lib.ptr(S), _lib.ptr(S0),
+                                             _lib.ptr(CEO), float(n_glob), float(svdTol), float(snrTol), int(bool(useSNR)),
+                                             float(meanE2), _lib.ptr(VtF), _lib.ptr(rhoVar), _lib.ptr(snr), _lib.ptr(invEv),
+                                             _lib.ptr(update), _lib.ptr(scalars), _lib.ptr(ws), ws.numel(), _lib.stream()))
+
+
+def chol_solve(S_destroyed, n, ld, F, x, info):
+    _lib.check(_lib.load().vmcpde_chol_solve(_lib.ptr(S_destroyed), int(n), int(ld), _lib.ptr(F), _lib.ptr(x), _lib.ptr(info),
+                                             _lib.stream()))
+
+
+def solve_scalars(S, S0, n, ld, F, update, meanE2, scalars, work2n):
+    _lib.check(_lib.load().vmcpde_solve_scalars(_lib.ptr(S), _lib.ptr(S0), int(n), int(ld), _lib.ptr(F), _lib.ptr(update),
+                                                float(meanE2), _lib.ptr(scalars), _lib.ptr(work2n), _lib.stream()))
+
+
+def obs_workspace(d):
+    nb = C.c_size_t(0)
+    _lib.check(_lib.load().vmcpde_observables_workspace_bytes(int(d), C.byref(nb)))
+    return empty(nb.value // 8 + 8)
+
+
+def obs_first(x, logp_, eloc, n, d, first, ws):
+    _lib.check(_lib.load().vmcpde_obs_first(_lib.ptr(x), _lib.ptr(logp_), _lib.ptr(eloc), int(n), int(d), _lib.ptr(first),
+                                            _lib.ptr(ws), _lib.stream()))
+
+
+def obs_central(x, n, d, mean, central, ws):
+    _lib.check(_lib.load().vmcpde_obs_central(_lib.ptr(x), int(n), int(d), _lib.ptr(mean), _lib.ptr(central), _lib.ptr(ws),
+                                              _lib.stream()))
+
+
+def ball_points(key, first, n, n_total, d, radius):
+    out = empty(n, d)
+    _lib.check(_lib.load().vmcpde_ball_points(int(key[0]), int(key[1]), int(first), int(n), int(n_total), int(d), float(radius),
+                                              _lib.ptr(out), _lib.stream()))
+    return out
+
+
+def sum_exp(logp_, n, out, ws):
+    _lib.check(_lib.load().vmcpde_sum_exp(_lib.ptr(logp_), int(n), _lib.ptr(out), _lib.ptr(ws), _lib.stream()))
+
+
+def dmma_peak_tflops():
+    v = C.c_double(0.0)
+    _lib.check(_lib.load().vmcpde_dmma_peak(C.byref(v)))
+    return v.value

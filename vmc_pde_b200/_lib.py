@@ -28,6 +28,7 @@ SIGNATURES = {
     "vmcpde_uniform": (C.c_int, [_u32, _u32, _i64, _i64, _i64, _vp, _vp]),
     "vmcpde_logp": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "vmcpde_local_terms": (C.c_int, [_vp, _vp, _vp, _i64, C.POINTER(Equation), _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "vmcpde_flow_transform": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "vmcpde_hessian": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "vmcpde_moments1": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp]),
     "vmcpde_center_force": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _dbl, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -35,6 +36,19 @@ SIGNATURES = {
     "vmcpde_sym_finalize": (C.c_int, [_vp, _i32, _dbl, _vp]),
     "vmcpde_diag_shift": (C.c_int, [_vp, _vp, _i32, _i32, _dbl, _vp]),
     "vmcpde_dmma_peak": (C.c_int, [C.POINTER(_dbl)]),
+    "vmcpde_gemm_tn": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i64, _dbl, _dbl, _vp]),
+    "vmcpde_eigh_workspace_bytes": (C.c_int, [_i32, _i32, C.POINTER(C.c_size_t)]),
+    "vmcpde_eigh": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "vmcpde_solve_tail_workspace_bytes": (C.c_int, [_i32, _i32, C.POINTER(C.c_size_t)]),
+    "vmcpde_solve_tail": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _dbl, _dbl, _dbl, _i32, _dbl,
+                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "vmcpde_chol_solve": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "vmcpde_solve_scalars": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _dbl, _vp, _vp, _vp]),
+    "vmcpde_observables_workspace_bytes": (C.c_int, [_i32, C.POINTER(C.c_size_t)]),
+    "vmcpde_obs_first": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "vmcpde_obs_central": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "vmcpde_ball_points": (C.c_int, [_u32, _u32, _i64, _i64, _i64, _i32, _dbl, _vp, _vp]),
+    "vmcpde_sum_exp": (C.c_int, [_vp, _i64, _vp, _vp, _vp]),
 }
 # filled in as later translation units land (solve / eigh / observables)
 OPTIONAL_SIGNATURES = {}

@@ -22,6 +22,8 @@ int set_error(int code, const std::string& msg) {
   extern template int launch_local_terms<Dv>(const FlowMeta&, const double*, const double*, long long, const EqParams&, \
                                              const double*, double*, double*, double*, double*, double*, long long,   \
                                              cudaStream_t);                                                           \
+  extern template int launch_transform<Dv>(const FlowMeta&, const double*, const double*, long long, int, double*,    \
+                                           double*, double*, cudaStream_t);                                           \
   extern template int launch_hessian<Dv>(const FlowMeta&, const double*, const double*, long long, double*, cudaStream_t);
 VMC_FOR_EACH_DIM(VMC_DECL)
 
@@ -138,6 +140,20 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_hessian(const vmcpd
   cudaStream_t s = (cudaStream_t)stream;
   switch (m.d) {
 #define X(Dv) VMC_CASE(Dv, (launch_hessian<D>(m, theta, x, n, H, s)))
+    VMC_FOR_EACH_DIM(X)
+#undef X
+  }
+  return set_error(VMCPDE_EUNSUPPORTED, "dimension not built");
+}
+
+extern "C" __attribute__((visibility("default"))) int vmcpde_flow_transform(const vmcpde_flow* f, const double* theta, const double* x,
+                                                                           int64_t n, int32_t inverse, double* y, double* logjac,
+                                                                           double* latent_logpdf_of_input, vmcpde_stream stream) {
+  VMC_REQUIRE(f && theta && x && y, "vmcpde_flow_transform: null pointer");
+  const FlowMeta& m = f->meta;
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (m.d) {
+#define X(Dv) VMC_CASE(Dv, (launch_transform<D>(m, theta, x, n, inverse, y, logjac, latent_logpdf_of_input, s)))
     VMC_FOR_EACH_DIM(X)
 #undef X
   }

@@ -182,6 +182,27 @@ hessian_kernel(const __grid_constant__ FlowMeta m, const double* __restrict__ th
   for (int a = 0; a < D * D; ++a) H[i * D * D + a] = Hl[a];
 }
 
+// INN map alone (net.py:168-182): y = INN(x) or INN^-1(x), its log-Jacobian, and log p_lat(x - offset)
+template <int D>
+__global__ void __launch_bounds__(kThreads)
+transform_kernel(const __grid_constant__ FlowMeta m, const double* __restrict__ theta, const double* __restrict__ x,
+                 long long n, int inv, double* __restrict__ y, double* __restrict__ logjac, double* __restrict__ lat_in,
+                 int use_smem) {
+  extern __shared__ double sth[];
+  const double* th = stage_theta(m, theta, sth, use_smem);
+  const long long i = blockIdx.x * (long long)kThreads + threadIdx.x;
+  if (i >= n) return;
+  double z[D], yin[D], lj = 0.0;
+#pragma unroll
+  for (int a = 0; a < D; ++a) { z[a] = x[i * D + a]; yin[a] = z[a] - m.offset[a]; }
+  if (lat_in) lat_in[i] = latent_logpdf<D>(m, th, yin);
+  if (inv) { for (int b = m.depth - 1; b >= 0; --b) lj += block_inverse_value<D>(m, th, b, z); }
+  else { for (int b = 0; b < m.depth; ++b) lj += block_forward_value<D>(m, th, b, z); }
+#pragma unroll
+  for (int a = 0; a < D; ++a) y[i * D + a] = z[a];
+  if (logjac) logjac[i] = lj;
+}
+
 // ------------------------------------------------------------------------------------------------
 template <class K>
 static int prep_smem(K kernel, size_t bytes) {
@@ -239,6 +260,21 @@ int launch_hessian(const FlowMeta& m, const double* theta, const double* x, long
   VMC_LAUNCH_CHECK("hessian_kernel");
   return 0;
 }
+
+template <int D>
+int launch_transform(const FlowMeta& m, const double* theta, const double* x, long long n, int inv, double* y,
+                     double* logjac, double* lat_in, cudaStream_t s) {
+  if (n <= 0) return 0;
+  const size_t tb = (size_t)m.P * 8;
+  const int use = tb <= kMaxThetaSmem;
+  const size_t smem = use ? tb : 0;
+  if (int rc = prep_smem(transform_kernel<D>, smem)) return rc;
+  transform_kernel<D><<<grid_for(n), kThreads, smem, s>>>(m, theta, x, n, inv, y, logjac, lat_in, use);
+  VMC_LAUNCH_CHECK("transform_kernel");
+  return 0;
+}
+template int launch_transform<VMC_DIM>(const FlowMeta&, const double*, const double*, long long, int, double*, double*,
+                                       double*, cudaStream_t);
 
 template int launch_sample<VMC_DIM>(const FlowMeta&, const double*, uint32_t, uint32_t, long long, long long, long long,
                                     const double*, double*, double*, double*, cudaStream_t);

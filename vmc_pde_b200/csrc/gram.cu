@@ -40,9 +40,12 @@ struct GramArgs {
   double* S[kMaxMats];
   const double* w[kMaxMats];
   int n_mats;
-  int tiles;      // Pp / 128
-  int Pp;
-  long long n;    // samples
+  int tiles;      // SYRK: Pp / 128 ; GEMM: tile rows (M / 128)
+  int tiles_n;    // GEMM: tile cols (N / 128)
+  int Pp;         // leading dimension of the outputs
+  int full;       // 0: upper-triangular tile pairs of X^T X ; 1: all tiles of X^T Y (second tensor map)
+  double alpha, beta;  // out = alpha * acc + beta * out
+  long long n;    // contraction length (samples)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -91,9 +94,11 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 
 // work item -> (matrix, tile row ti <= tile col tj); matrices innermost so the weighted variants of one
 // tile pair run side by side and share both panels in L2
-__device__ __forceinline__ void decode_item(long long item, int n_mats, int tiles, int& mat, int& ti, int& tj) {
+__device__ __forceinline__ void decode_item(long long item, const GramArgs& a, int& mat, int& ti, int& tj) {
+  const int n_mats = a.n_mats, tiles = a.tiles;
   mat = (int)(item % n_mats);
   long long p = item / n_mats;
+  if (a.full) { ti = (int)(p / a.tiles_n); tj = (int)(p % a.tiles_n); return; }
   // row-major enumeration of the upper triangle: row ti has (tiles - ti) entries
   int r = 0;
   long long rem = p;
@@ -104,7 +109,8 @@ __device__ __forceinline__ void decode_item(long long item, int n_mats, int tile
 }
 
 __global__ void __launch_bounds__(kGramThreads, 1)
-gram_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ GramArgs args) {
+gram_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmapB,
+            const __grid_constant__ GramArgs args) {
   // dynamic shared memory is the only shared allocation, so it starts 1 KB aligned (128B-swizzle atom)
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full = (uint64_t*)(smem + kStages * kStageBytes);
@@ -117,7 +123,8 @@ gram_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Gr
   }
   __syncthreads();
 
-  const long long n_items = (long long)args.n_mats * args.tiles * (args.tiles + 1) / 2;
+  const long long n_items = args.full ? (long long)args.n_mats * args.tiles * args.tiles_n
+                                      : (long long)args.n_mats * args.tiles * (args.tiles + 1) / 2;
   const int k_iters = (int)(args.n / kKC);
 
   if (warp >= kConsumerWarps) {
@@ -128,8 +135,8 @@ gram_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Gr
       uint32_t phase = 0;
       for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
         int mat, ti, tj;
-        decode_item(item, args.n_mats, args.tiles, mat, ti, tj);
-        const bool diag = (ti == tj);
+        decode_item(item, args, mat, ti, tj);
+        const bool diag = !args.full && (ti == tj);
         const double* w = args.w[mat];
         const uint32_t bytes = kPanelBytes + (diag ? 0 : kPanelBytes) + (w ? kWBytes : 0);
         for (int k = 0; k < k_iters; ++k) {
@@ -137,7 +144,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Gr
           uint8_t* st = smem + stage * kStageBytes;
           mbar_expect_tx(&full[stage], bytes);
           tma_load_3d(st, &tmap, &full[stage], 0, k * kKC, ti * (kBM / 16));
-          if (!diag) tma_load_3d(st + kPanelBytes, &tmap, &full[stage], 0, k * kKC, tj * (kBN / 16));
+          if (!diag) tma_load_3d(st + kPanelBytes, args.full ? &tmapB : &tmap, &full[stage], 0, k * kKC, tj * (kBN / 16));
           if (w) bulk_load_1d(st + 2 * kPanelBytes, w + (long long)k * kKC, kWBytes, &full[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -167,8 +174,8 @@ gram_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Gr
   uint32_t phase = 0;
   for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
     int mat, ti, tj;
-    decode_item(item, args.n_mats, args.tiles, mat, ti, tj);
-    const bool diag = (ti == tj);
+    decode_item(item, args, mat, ti, tj);
+    const bool diag = !args.full && (ti == tj);
     const bool weighted = args.w[mat] != nullptr;
     double acc[8][4][2];
 #pragma unroll
@@ -217,9 +224,10 @@ gram_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Gr
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         double2* p = (double2*)(S + (row0 + i * 8) * args.Pp + col0 + j * 8);
-        double2 v = *p;
-        v.x += acc[i][j][0];
-        v.y += acc[i][j][1];
+        double2 v = make_double2(0.0, 0.0);
+        if (args.beta != 0.0) { v = *p; v.x *= args.beta; v.y *= args.beta; }
+        v.x = fma(args.alpha, acc[i][j][0], v.x);
+        v.y = fma(args.alpha, acc[i][j][1], v.y);
         *p = v;
       }
   }
@@ -294,7 +302,7 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_gram(const double* 
     a.w[m] = weights ? weights[m] : nullptr;
     VMC_REQUIRE(((uintptr_t)a.w[m] & 15) == 0, "vmcpde_gram: weights must be 16-byte aligned");
   }
-  a.n_mats = n_mats; a.tiles = Pp / 128; a.Pp = Pp; a.n = n;
+  a.n_mats = n_mats; a.tiles = Pp / 128; a.tiles_n = Pp / 128; a.Pp = Pp; a.n = n; a.full = 0; a.alpha = 1.0; a.beta = 1.0;
   CUtensorMap map;
   if (int rc = make_panel_tensor_map(&map, O, n, ldo, Pp)) return rc;
   const size_t smem = gram_smem_bytes();
@@ -306,8 +314,36 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_gram(const double* 
   const long long n_items = (long long)n_mats * a.tiles * (a.tiles + 1) / 2;
   int grid = num_sms();
   if (n_items < grid) grid = (int)n_items;
-  gram_kernel<<<grid, kGramThreads, smem, (cudaStream_t)stream>>>(map, a);
+  gram_kernel<<<grid, kGramThreads, smem, (cudaStream_t)stream>>>(map, map, a);
   VMC_LAUNCH_CHECK("gram_kernel");
+  return 0;
+}
+
+// General FP64 tensor-core product on the same pipeline: Out[M x N] = alpha * X^T Y + beta * Out with
+// X [K x M] (ldx), Y [K x N] (ldy) row-major, i.e. both operands contiguous along the output index
+// (the layout every product of the solve stage is arranged to have).  M, N multiples of 128, K of 16.
+extern "C" __attribute__((visibility("default"))) int vmcpde_gemm_tn(const double* X, int64_t ldx, const double* Y, int64_t ldy, double* Out,
+                                                                      int64_t ldo, int32_t M, int32_t N, int64_t K, double alpha, double beta,
+                                                                      vmcpde_stream stream) {
+  using namespace vmc;
+  VMC_REQUIRE(X && Y && Out, "vmcpde_gemm_tn: null pointer");
+  VMC_REQUIRE(M > 0 && N > 0 && M % 128 == 0 && N % 128 == 0 && K >= 0 && K % kKC == 0, "vmcpde_gemm_tn: M, N multiples of 128 and K of 16 required");
+  VMC_REQUIRE(ldx >= M && ldy >= N && ldo >= N && ldx % 2 == 0 && ldy % 2 == 0 && ldo % 2 == 0, "vmcpde_gemm_tn: bad leading dimensions");
+  VMC_REQUIRE(ldo <= 0x7fffffff, "vmcpde_gemm_tn: ldo too large");
+  if (K == 0) return 0;
+  GramArgs a{};
+  a.S[0] = Out; a.w[0] = nullptr; a.n_mats = 1; a.tiles = M / 128; a.tiles_n = N / 128; a.Pp = (int)ldo; a.n = K; a.full = 1;
+  a.alpha = alpha; a.beta = beta;
+  CUtensorMap mx, my;
+  if (int rc = make_panel_tensor_map(&mx, X, K, ldx, M)) return rc;
+  if (int rc = make_panel_tensor_map(&my, Y, K, ldy, N)) return rc;
+  const size_t smem = gram_smem_bytes();
+  VMC_CUDA_CHECK(cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long n_items = (long long)a.tiles * a.tiles_n;
+  int grid = num_sms();
+  if (n_items < grid) grid = (int)n_items;
+  gram_kernel<<<grid, kGramThreads, smem, (cudaStream_t)stream>>>(mx, my, a);
+  VMC_LAUNCH_CHECK("gram_kernel(gemm_tn)");
   return 0;
 }
 

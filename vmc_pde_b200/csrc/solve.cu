@@ -1,0 +1,388 @@
+// Regularised solve of the TDVP equation on the device.
+//  * vmcpde_solve_tail: everything after the eigendecomposition in tdvp.py:66-94 -- V^T F, the signal-to-noise
+//    ratio (tdvp.py:68-71, computed as diag(V^T C V) with C the dE^2-weighted Gram instead of the reference's
+//    N x P x P product EOdata @ V), eigenvalue cut-offs, update = V (invEv * reg * V^T F), solver residual
+//    and TDVP error.
+//  * vmcpde_chol_solve: blocked Cholesky fast path for a shifted (positive definite) S
+//    (north-star item 4; admissible only with diagonalShift > 0).
+#include <cstdint>
+#include "common.cuh"
+
+extern "C" int vmcpde_gemm_tn(const double* X, int64_t ldx, const double* Y, int64_t ldy, double* Out, int64_t ldo,
+                              int32_t M, int32_t N, int64_t K, double alpha, double beta, vmcpde_stream stream);
+
+namespace vmc {
+
+__device__ __forceinline__ double wsum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double bsum(double v, double* sh) {  // broadcast block sum, sh >= 33 doubles
+  v = wsum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  double r = (lane < nw) ? sh[lane] : 0.0;
+  return wsum(r);
+}
+
+// y[r] = sum_c A[r][c] x[c]   (warp per row)
+__global__ void __launch_bounds__(256) gemv_rows_kernel(const double* __restrict__ A, int ld, int m, int n,
+                                                        const double* __restrict__ x, double* __restrict__ y) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < m; r += gridDim.x * wpb) {
+    const double* row = A + (size_t)r * ld;
+    double s0 = 0.0, s1 = 0.0;
+    int c = lane;
+    for (; c + 32 < n; c += 64) { s0 = fma(row[c], x[c], s0); s1 = fma(row[c + 32], x[c + 32], s1); }
+    if (c < n) s0 = fma(row[c], x[c], s0);
+    const double s = wsum(s0 + s1);
+    if (lane == 0) y[r] = s;
+  }
+}
+
+// y[c] = sum_r A[r][c] x[r]   (CTA owns 32 columns, 8 warps stride over rows)
+__global__ void __launch_bounds__(256) gemv_cols_kernel(const double* __restrict__ A, int ld, int m, int n,
+                                                        const double* __restrict__ x, double* __restrict__ y) {
+  __shared__ double sh[8][33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 32 + lane;
+  double a0 = 0.0, a1 = 0.0;
+  if (c < n) {
+    int r = warp;
+    for (; r + 8 < m; r += 16) { a0 = fma(A[(size_t)r * ld + c], x[r], a0); a1 = fma(A[(size_t)(r + 8) * ld + c], x[r + 8], a1); }
+    if (r < m) a0 = fma(A[(size_t)r * ld + c], x[r], a0);
+  }
+  sh[warp][lane] = a0 + a1;
+  __syncthreads();
+  if (warp == 0 && c < n) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += sh[w][lane];
+    y[c] = s;
+  }
+}
+
+// out[c] = sum_r A[r][c] * B[r][c]
+__global__ void __launch_bounds__(256) coldot_kernel(const double* __restrict__ A, const double* __restrict__ B, int ld,
+                                                     int m, int n, double* __restrict__ out) {
+  __shared__ double sh[8][33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 32 + lane;
+  double a0 = 0.0;
+  if (c < n)
+    for (int r = warp; r < m; r += 8) a0 = fma(A[(size_t)r * ld + c], B[(size_t)r * ld + c], a0);
+  sh[warp][lane] = a0;
+  __syncthreads();
+  if (warp == 0 && c < n) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += sh[w][lane];
+    out[c] = s;
+  }
+}
+
+// B[c][r] = A[r][c] on the ld x ld padded square (32x32 tiles)
+__global__ void __launch_bounds__(256) transpose_kernel(const double* __restrict__ A, double* __restrict__ B, int ld) {
+  __shared__ double tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int r = ty; r < 32; r += 8) tile[r][tx] = A[(size_t)(r0 + r) * ld + c0 + tx];
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) B[(size_t)(c0 + r) * ld + r0 + tx] = tile[tx][r];
+}
+
+// tdvp.py:70-71,82-89: rhoVar, snr, invEv, regulariser -> coefficient in the eigenbasis
+__global__ void solve_coef_kernel(const double* __restrict__ ev, const double* __restrict__ VtF,
+                                  const double* __restrict__ q, int n, double n_glob, double svdTol, double snrTol,
+                                  int useSNR, double* __restrict__ rhoVar, double* __restrict__ snr,
+                                  double* __restrict__ invEv, double* __restrict__ coef) {
+  const double evmax = ev[n - 1];
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const double f = VtF[k];
+    double sn = 0.0;
+    if (q) {
+      const double rv = q[k] - f * f;  // population variance of (dE * dO) . v_k
+      rhoVar[k] = rv;
+      sn = sqrt(fabs(n_glob * f * f / rv));
+      snr[k] = sn;
+    }
+    const double r = fabs(ev[k] / evmax);
+    const double inv = r > 1e-14 ? 1.0 / ev[k] : 0.0;
+    const double t = svdTol / r, t2 = t * t;
+    double reg = 1.0 / (1.0 + t2 * t2 * t2);
+    if (useSNR) { const double u = snrTol / sn, u2 = u * u; reg *= 1.0 / (1.0 + u2 * u2 * u2); }
+    invEv[k] = inv;
+    coef[k] = inv * reg * f;
+  }
+}
+
+// scalars[0] = ||S u - F|| / ||F|| ; scalars[1] = 1 + (u.S0u - 2 F0.u) / meanE2   (tdvp.py:93-94)
+__global__ void __launch_bounds__(1024) solve_scalars_kernel(const double* __restrict__ Su, const double* __restrict__ S0u,
+                                                             const double* __restrict__ F, const double* __restrict__ u,
+                                                             int n, double meanE2, double* __restrict__ scalars) {
+  __shared__ double sh[33];
+  double a = 0.0, b = 0.0, c = 0.0, d = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double r = Su[i] - F[i];
+    a += r * r; b += F[i] * F[i]; c += u[i] * S0u[i]; d += F[i] * u[i];
+  }
+  a = bsum(a, sh); b = bsum(b, sh); c = bsum(c, sh); d = bsum(d, sh);
+  if (threadIdx.x == 0) {
+    scalars[0] = sqrt(a) / sqrt(b);
+    scalars[1] = 1.0 + (c - 2.0 * d) / meanE2;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Blocked Cholesky (lower), nb = 64
+constexpr int kNb = 64;
+
+__global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A, int ld, int j0, int nb, int* info) {
+  __shared__ double L[kNb][kNb + 1];
+  for (int idx = threadIdx.x; idx < nb * nb; idx += blockDim.x) {
+    const int r = idx / nb, c = idx % nb;
+    L[r][c] = A[(size_t)(j0 + r) * ld + j0 + c];
+  }
+  __syncthreads();
+  for (int j = 0; j < nb; ++j) {
+    if (threadIdx.x == 0) {
+      const double p = L[j][j];
+      if (!(p > 0.0)) { if (*info == 0) *info = j0 + j + 1; L[j][j] = 1.0; } else L[j][j] = sqrt(p);
+    }
+    __syncthreads();
+    const double d = L[j][j];
+    for (int i = j + 1 + threadIdx.x; i < nb; i += blockDim.x) L[i][j] /= d;
+    __syncthreads();
+    const int m = nb - j - 1;
+    for (int idx = threadIdx.x; idx < m * m; idx += blockDim.x) {
+      const int i = j + 1 + idx / m, k = j + 1 + idx % m;
+      if (k <= i) L[i][k] -= L[i][j] * L[k][j];
+    }
+    __syncthreads();
+  }
+  for (int idx = threadIdx.x; idx < nb * nb; idx += blockDim.x) {
+    const int r = idx / nb, c = idx % nb;
+    A[(size_t)(j0 + r) * ld + j0 + c] = (c <= r) ? L[r][c] : 0.0;
+  }
+}
+
+// rows below the diagonal block: X L11^T = A21, thread per row
+__global__ void __launch_bounds__(64) trsm_panel_kernel(double* __restrict__ A, int ld, int n, int j0, int nb) {
+  __shared__ double L[kNb][kNb + 1];
+  for (int idx = threadIdx.x; idx < nb * nb; idx += blockDim.x) L[idx / nb][idx % nb] = A[(size_t)(j0 + idx / nb) * ld + j0 + idx % nb];
+  __syncthreads();
+  const int r = j0 + nb + blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  double x[kNb];
+  double* row = A + (size_t)r * ld + j0;
+#pragma unroll 4
+  for (int c = 0; c < nb; ++c) {
+    double s = row[c];
+    for (int k = 0; k < c; ++k) s -= x[k] * L[c][k];
+    x[c] = s / L[c][c];
+  }
+  for (int c = 0; c < nb; ++c) row[c] = x[c];
+}
+
+// trailing update, lower tiles: A22[r][c] -= sum_k L21[r][k] L21[c][k]   (64x64 tiles, DMMA, K = nb)
+__device__ __forceinline__ void dmma_s(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__global__ void __launch_bounds__(128) syrk_update_kernel(double* __restrict__ A, int ld, int n, int j0, int nb) {
+  constexpr int KC = 32;
+  __shared__ double Ls[64][KC + 4], Rs[64][KC + 4];
+  const int t0 = j0 + nb;
+  const int tr = blockIdx.y, tc = blockIdx.x;
+  if (tc > tr) return;
+  const int r0 = t0 + tr * 64, c0 = t0 + tc * 64;
+  if (r0 >= n) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int wm = warp >> 1, wn = warp & 1;
+  double acc[4][4][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { acc[a][c][0] = 0.0; acc[a][c][1] = 0.0; }
+  for (int kk = 0; kk < nb; kk += KC) {
+    for (int idx = threadIdx.x; idx < 64 * KC; idx += blockDim.x) {
+      const int r = idx / KC, k = idx % KC;
+      const bool kin = kk + k < nb;
+      Ls[r][k] = (kin && r0 + r < n) ? A[(size_t)(r0 + r) * ld + j0 + kk + k] : 0.0;
+      Rs[r][k] = (kin && c0 + r < n) ? A[(size_t)(c0 + r) * ld + j0 + kk + k] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k0 = 0; k0 < KC; k0 += 4) {
+      double a[4], b[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { a[q] = Ls[wm * 32 + q * 8 + g][k0 + t]; b[q] = Rs[wn * 32 + q * 8 + g][k0 + t]; }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) dmma_s(acc[q][p][0], acc[q][p][1], a[q], b[p]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int r = r0 + wm * 32 + q * 8 + g;
+    if (r >= n) continue;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int c = c0 + wn * 32 + p * 8 + 2 * t;
+      if (c < n && c <= r) A[(size_t)r * ld + c] -= acc[q][p][0];
+      if (c + 1 < n && c + 1 <= r) A[(size_t)r * ld + c + 1] -= acc[q][p][1];
+    }
+  }
+}
+
+// L y = b then L^T x = y, single CTA; diagonal blocks are staged in shared memory and solved by warp 0
+__global__ void __launch_bounds__(1024) chol_substitute_kernel(const double* __restrict__ L, int ld, int n,
+                                                               const double* __restrict__ b, double* __restrict__ x) {
+  __shared__ double blk[kNb];
+  __shared__ double Ld[kNb][kNb + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) x[i] = b[i];
+  __syncthreads();
+  for (int j0 = 0; j0 < n; j0 += kNb) {  // forward
+    const int nb = min(kNb, n - j0);
+    for (int idx = threadIdx.x; idx < nb * nb; idx += blockDim.x) Ld[idx / nb][idx % nb] = L[(size_t)(j0 + idx / nb) * ld + j0 + idx % nb];
+    if ((int)threadIdx.x < nb) blk[threadIdx.x] = x[j0 + threadIdx.x];
+    __syncthreads();
+    if (warp == 0) {
+      for (int r = 0; r < nb; ++r) {
+        double s = 0.0;
+        for (int k = lane; k < r; k += 32) s += Ld[r][k] * blk[k];
+        s = wsum(s);
+        if (lane == 0) blk[r] = (blk[r] - s) / Ld[r][r];
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < nb) x[j0 + threadIdx.x] = blk[threadIdx.x];
+    for (int r = j0 + nb + threadIdx.x; r < n; r += blockDim.x) {
+      const double* row = L + (size_t)r * ld + j0;
+      double s = 0.0;
+      for (int k = 0; k < nb; ++k) s = fma(row[k], blk[k], s);
+      x[r] -= s;
+    }
+    __syncthreads();
+  }
+  for (int j0 = ((n - 1) / kNb) * kNb; j0 >= 0; j0 -= kNb) {  // backward with L^T
+    const int nb = min(kNb, n - j0);
+    for (int idx = threadIdx.x; idx < nb * nb; idx += blockDim.x) Ld[idx / nb][idx % nb] = L[(size_t)(j0 + idx / nb) * ld + j0 + idx % nb];
+    if ((int)threadIdx.x < nb) blk[threadIdx.x] = x[j0 + threadIdx.x];
+    __syncthreads();
+    if (warp == 0) {
+      for (int r = nb - 1; r >= 0; --r) {
+        double s = 0.0;
+        for (int k = r + 1 + lane; k < nb; k += 32) s += Ld[k][r] * blk[k];
+        s = wsum(s);
+        if (lane == 0) blk[r] = (blk[r] - s) / Ld[r][r];
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < nb) x[j0 + threadIdx.x] = blk[threadIdx.x];
+    for (int c = threadIdx.x; c < j0; c += blockDim.x) {
+      double s = 0.0;
+      for (int k = 0; k < nb; ++k) s = fma(L[(size_t)(j0 + k) * ld + c], blk[k], s);
+      x[c] -= s;
+    }
+    __syncthreads();
+  }
+}
+
+static size_t al(size_t x) { return (x + 255) / 256 * 256; }
+
+}  // namespace vmc
+
+using namespace vmc;
+
+extern "C" __attribute__((visibility("default"))) int vmcpde_solve_tail_workspace_bytes(int32_t n, int32_t ld, size_t* bytes) {
+  VMC_REQUIRE(bytes && n >= 1 && ld >= n, "vmcpde_solve_tail_workspace_bytes: bad arguments");
+  *bytes = 2 * al((size_t)ld * ld * 8) + 6 * al((size_t)ld * 8);
+  return 0;
+}
+
+// Everything after eigh in TDVP.solve / transform_to_eigenbasis (tdvp.py:66-94).
+// ev[n] ascending, VT[n x ld] rows = eigenvectors (pad region zero), F[n], S (shifted) and S0 [n x ld] full symmetric,
+// CEO [ld x ld] = (1/N) sum dE^2 dO dO^T (padded, zero pad) or NULL to skip the SNR.
+// Outputs: VtF, rhoVar, snr (NULL-able when CEO is NULL), invEv, update (n each), scalars[2] = {residual, tdvp_error}.
+extern "C" __attribute__((visibility("default"))) int vmcpde_solve_tail(
+    const double* ev, const double* VT, int32_t n, int32_t ld, const double* F, const double* S, const double* S0,
+    const double* CEO, double n_glob, double svdTol, double snrTol, int32_t useSNR, double meanE2, double* VtF,
+    double* rhoVar, double* snr, double* invEv, double* update, double* scalars, void* workspace,
+    size_t workspace_bytes, vmcpde_stream stream) {
+  VMC_REQUIRE(ev && VT && F && S && S0 && VtF && invEv && update && scalars && workspace, "vmcpde_solve_tail: null pointer");
+  VMC_REQUIRE(!useSNR || CEO, "vmcpde_solve_tail: useSNR needs the SNR covariance");
+  VMC_REQUIRE(!CEO || (rhoVar && snr), "vmcpde_solve_tail: rhoVar/snr outputs required with CEO");
+  VMC_REQUIRE(!CEO || ld % 128 == 0, "vmcpde_solve_tail: ld must be a multiple of 128");
+  size_t need = 0;
+  vmcpde_solve_tail_workspace_bytes(n, ld, &need);
+  VMC_REQUIRE(workspace_bytes >= need, "vmcpde_solve_tail: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  uint8_t* wp = (uint8_t*)workspace;
+  double* V = (double*)wp; wp += al((size_t)ld * ld * 8);
+  double* W = (double*)wp; wp += al((size_t)ld * ld * 8);
+  double* q = (double*)wp; wp += al((size_t)ld * 8);
+  double* coef = (double*)wp; wp += al((size_t)ld * 8);
+  double* Su = (double*)wp; wp += al((size_t)ld * 8);
+  double* S0u = (double*)wp; wp += al((size_t)ld * 8);
+  const int sms = num_sms();
+  const int rb = max(1, min(sms * 4, (n + 7) / 8));
+  gemv_rows_kernel<<<rb, 256, 0, s>>>(VT, ld, n, n, F, VtF);
+  if (CEO) {
+    transpose_kernel<<<dim3(ld / 32, ld / 32), 256, 0, s>>>(VT, V, ld);
+    if (int rc = vmcpde_gemm_tn(CEO, ld, V, ld, W, ld, ld, ld, ld, 1.0, 0.0, stream)) return rc;
+    coldot_kernel<<<(n + 31) / 32, 256, 0, s>>>(V, W, ld, n, n, q);
+  }
+  solve_coef_kernel<<<max(1, min(sms, (n + 255) / 256)), 256, 0, s>>>(ev, VtF, CEO ? q : nullptr, n, n_glob, svdTol, snrTol,
+                                                                    useSNR, rhoVar, snr, invEv, coef);
+  gemv_cols_kernel<<<(n + 31) / 32, 256, 0, s>>>(VT, ld, n, n, coef, update);
+  gemv_rows_kernel<<<rb, 256, 0, s>>>(S, ld, n, n, update, Su);
+  gemv_rows_kernel<<<rb, 256, 0, s>>>(S0, ld, n, n, update, S0u);
+  solve_scalars_kernel<<<1, 1024, 0, s>>>(Su, S0u, F, update, n, meanE2, scalars);
+  VMC_LAUNCH_CHECK("solve_tail");
+  return 0;
+}
+
+// Solve S x = F by blocked Cholesky.  S (n x n, ld) is overwritten by its lower factor.  info (device int, must be
+// zero on entry) receives 1 + index of the first non-positive pivot; the caller checks it after synchronising.
+// scalars[2] (optional) = {residual ||S x - F||/||F||, tdvp_error} need S_copy / S0 / meanE2 like solve_tail.
+extern "C" __attribute__((visibility("default"))) int vmcpde_chol_solve(double* S, int32_t n, int32_t ld, const double* F,
+                                                                       double* x, int32_t* info, vmcpde_stream stream) {
+  VMC_REQUIRE(S && F && x && info, "vmcpde_chol_solve: null pointer");
+  VMC_REQUIRE(n >= 1 && ld >= n, "vmcpde_chol_solve: bad dimensions");
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int j0 = 0; j0 < n; j0 += kNb) {
+    const int nb = min(kNb, n - j0);
+    potrf_diag_kernel<<<1, 256, 0, s>>>(S, ld, j0, nb, info);
+    const int rem = n - j0 - nb;
+    if (rem > 0) {
+      trsm_panel_kernel<<<(rem + 63) / 64, 64, 0, s>>>(S, ld, n, j0, nb);
+      const int tiles = (rem + 63) / 64;
+      syrk_update_kernel<<<dim3(tiles, tiles), 128, 0, s>>>(S, ld, n, j0, nb);
+    }
+  }
+  chol_substitute_kernel<<<1, 1024, 0, s>>>(S, ld, n, F, x);
+  VMC_LAUNCH_CHECK("chol_solve");
+  return 0;
+}
+
+// residual and TDVP error for a given update (used by the Cholesky path): scalars = {||S u - F||/||F||, tdvp_error}
+extern "C" __attribute__((visibility("default"))) int vmcpde_solve_scalars(const double* S, const double* S0, int32_t n, int32_t ld,
+                                                                          const double* F, const double* update, double meanE2,
+                                                                          double* scalars, double* work2n, vmcpde_stream stream) {
+  VMC_REQUIRE(S && S0 && F && update && scalars && work2n, "vmcpde_solve_scalars: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int rb = max(1, min(num_sms() * 4, (n + 7) / 8));
+  gemv_rows_kernel<<<rb, 256, 0, s>>>(S, ld, n, n, update, work2n);
+  gemv_rows_kernel<<<rb, 256, 0, s>>>(S0, ld, n, n, update, work2n + n);
+  solve_scalars_kernel<<<1, 1024, 0, s>>>(work2n, work2n + n, F, update, n, meanE2, scalars);
+  VMC_LAUNCH_CHECK("solve_scalars");
+  return 0;
+}

@@ -1,0 +1,349 @@
+"""Mirror of vmc_fluids/tdvp.py: the TDVP right-hand side  theta_dot = S^-1 F  with the reference's regularised
+eigen-solve, computed entirely on the GPU.
+
+`TDVP.__call__(netParameters, t, psi=, evolutionEq=, nSamplesTDVP=, nSamplesObs=, timings=, ...)` keeps the
+reference's signature, required keys and post-call attributes (tdvp.py:96-164).  What changes is
+how the numbers are produced:
+
+  * samples are processed in chunks; the N x P matrix O is never required to exist as a whole and the reference's
+    other N x P temporaries (centred O, E*O, logp*O, EO@V; tdvp.py:30-34,40-47,68) never exist at all;
+  * two passes: first moments (one packed all-reduce), then centring + force vector + the three weighted Grams
+    S0, SExp, C_EO on FP64 tensor cores (one packed all-reduce) -- the reference issues ten host-staged Allreduces;
+  * the signal-to-noise ratio uses diag(V^T C_EO V) instead of the N x P x P product EOdata @ V (tdvp.py:68-70);
+  * eigendecomposition, cut-offs, update, residual and TDVP error run on the device (no host LAPACK round trip).
+"""
+from dataclasses import dataclass
+import math
+import time
+import numpy as np
+import scipy.special
+import torch
+
+from . import _kernels, mpi_wrapper as mpi, global_defs
+
+
+@dataclass
+class TDVP:
+    useSNR: bool = False
+    snrTol: float = 2e0
+    svdTol: float = 1e-11
+    diagonalShift: float = 0
+    diagonalizeOnDevice: bool = False   # kept for signature parity; the solve is always on the device
+    # ---- extensions (not in the reference; defaults reproduce the reference's semantics) ----
+    solver: str = "eigh"               # "eigh" | "cholesky" (needs diagonalShift > 0; no ev / V / snr)
+    computeSExp: bool = True           # SExp is only read by AdaptiveHeun (stepper.py:71)
+    computeSNR: bool = True            # snr is logged by main.py:187 and gates the solve when useSNR
+    chunkSamples: int = 0              # samples per chunk (0 = choose from free memory)
+    memoryFraction: float = 0.45       # share of free device memory the O buffer may take
+
+    def __post_init__(self):
+        if self.solver not in ("eigh", "cholesky"):
+            raise ValueError("solver must be 'eigh' or 'cholesky'")
+        self._bufP = None
+        self.gpu_launches = 0
+        self.S = self.S0 = self.F0 = self.SExp = self.ev = self.V = self.VtF = None
+        self.rhoVar = self.snr = self.invEv = None
+        self.solverResidual = self.tdvp_error = None
+        self.ElocMean = self.ElocMeanAbs = self.ElocVar = None
+
+    # ------------------------------------------------------------------------------------------------
+    def _buffers(self, P, Pp):
+        if self._bufP != (P, Pp):
+            z = _kernels.zeros
+            self._second = z(3 * Pp * Pp + Pp + 8)            # [S0 | SExp | CEO | Fsum | var_sum] packed for one all-reduce
+            self._Sshift = None
+            self._Swork = _kernels.empty(Pp, Pp)
+            self._VT = z(Pp, Pp)
+            self._vecs = z(8, Pp)                            # ev, VtF, rhoVar, snr, invEv, update, 2 x scratch
+            self._scal = z(2)
+            self._info = torch.zeros(1, dtype=torch.int32, device=global_defs.device())
+            self._bufP = (P, Pp)
+        return self._second
+
+    def _mats(self, Pp):
+        s = self._second
+        S0 = s[0:Pp * Pp].view(Pp, Pp)
+        SExp = s[Pp * Pp:2 * Pp * Pp].view(Pp, Pp)
+        CEO = s[2 * Pp * Pp:3 * Pp * Pp].view(Pp, Pp)
+        Fsum = s[3 * Pp * Pp:3 * Pp * Pp + Pp]
+        var_sum = s[3 * Pp * Pp + Pp:3 * Pp * Pp + Pp + 1]
+        return S0, SExp, CEO, Fsum, var_sum
+
+    # ---- pieces of get_tdvp_equation (tdvp.py:36-52) on one chunk ------------------------------------
+    def _pass1_chunk(self, E, lp, O, n, ldo, first):
+        _kernels.moments1(E, lp, O, n, ldo, first)
+        self.gpu_launches += 1
+
+    def _pass2_chunk(self, E, lp, O, n, n_pad, ldo, Pp, meanO, meanE, scratch):
+        S0, SExp, CEO, Fsum, var_sum = self._mats(Pp)
+        dE, wE, wLp = scratch
+        if n_pad > n:
+            O[n:n_pad].zero_(); wE[n:n_pad].zero_(); wLp[n:n_pad].zero_()
+        _kernels.center_force(O, n, ldo, meanO, E, lp, meanE, dE, wE, wLp, Fsum, var_sum)
+        mats, weights = [S0], [None]
+        if self.computeSExp:
+            mats.append(SExp); weights.append(wLp)
+        if self.computeSNR and self.solver == "eigh":
+            mats.append(CEO); weights.append(wE)
+        _kernels.gram(O, n_pad, ldo, Pp, weights, mats)
+        self.gpu_launches += 2
+
+    def _finish(self, P, Pp, N, first):
+        """All-reduce of the second moments, normalisation, regularised solve (tdvp.py:50-51,57-94)."""
+        S0, SExp, CEO, Fsum, var_sum = self._mats(Pp)
+        mpi.allreduce_(self._second)
+        inv = 1.0 / N
+        _kernels.sym_finalize(S0, Pp, inv)
+        if self.computeSExp:
+            _kernels.sym_finalize(SExp, Pp, inv)
+        use_ceo = self.computeSNR and self.solver == "eigh"
+        if use_ceo:
+            _kernels.sym_finalize(CEO, Pp, inv)
+        F = Fsum * inv
+        self.ElocVar = (var_sum[0] * inv).clone()
+        self.S0, self.F0 = S0[:P, :P], F[:P]
+        self.SExp = SExp[:P, :P] if self.computeSExp else None
+        S = S0
+        if self.diagonalShift > 1e-10:  # tdvp.py:50-51
+            if self._Sshift is None:
+                self._Sshift = _kernels.empty(Pp, Pp)
+            _kernels.diag_shift(S0, self._Sshift, Pp, P, self.diagonalShift)
+            S = self._Sshift
+        self.S = S[:P, :P]
+        meanE2 = float(first[2]) * inv  # mean(Eloc**2) of the un-centred local term (tdvp.py:93); host scalar
+        ev, VtF, rhoVar, snr, invEv, update, w0, w1 = [self._vecs[i] for i in range(8)]
+        self._Swork.copy_(S)
+        if self.solver == "eigh":
+            ws = _kernels.workspace(_kernels.eigh_workspace_bytes(P, Pp))
+            _kernels.eigh(self._Swork, P, Pp, ev, self._VT, ws)
+            _kernels.solve_tail(ev, self._VT, P, Pp, F, S, S0, CEO if use_ceo else None, float(N), self.svdTol, self.snrTol,
+                                self.useSNR, meanE2, VtF, rhoVar if use_ceo else None, snr if use_ceo else None, invEv, update,
+                                self._scal, ws)
+            self.ev, self.V, self.VtF, self.invEv = ev[:P], self._VT[:P, :P].T, VtF[:P], invEv[:P]
+            self.rhoVar, self.snr = (rhoVar[:P], snr[:P]) if use_ceo else (None, None)
+        else:
+            if not self.diagonalShift > 1e-10:
+                raise ValueError("solver='cholesky' needs diagonalShift > 0: S is rank deficient otherwise (SURVEY fact 5)")
+            self._info.zero_()
+            _kernels.chol_solve(self._Swork, P, Pp, F, update, self._info)
+            _kernels.solve_scalars(S, S0, P, Pp, F, update, meanE2, self._scal, self._vecs[6:8].reshape(-1))
+            if int(self._info.item()) != 0:
+                raise RuntimeError(f"Cholesky failed: non-positive pivot at index {int(self._info.item()) - 1}")
+            self.ev = self.V = self.VtF = self.invEv = self.rhoVar = self.snr = None
+        self.gpu_launches += 8
+        self.solverResidual, self.tdvp_error = self._scal[0].clone(), self._scal[1].clone()
+        return update[:P].clone()
+
+    # ---- reference entry points on materialised arrays -----------------------------------------------
+    def get_tdvp_equation(self, Eloc, gradients, logProbs):
+        """tdvp.py:36-52 for given (1,n), (1,n,P), (1,n) arrays; returns (S, F, EOdata)."""
+        self._solve_materialised(Eloc, gradients, logProbs, solve=False)
+        dE = (_kernels.as_dev(Eloc) - self.ElocMean)
+        EO = dE[..., None] * (_kernels.as_dev(gradients) - self._gradMean[None, None, :])
+        return self.S, self.F0, EO
+
+    def solve(self, Eloc, gradients, logProbs):
+        """tdvp.py:73-94: returns (update, solverResidual, tdvp_error)."""
+        update = self._solve_materialised(Eloc, gradients, logProbs, solve=True)
+        return update, self.solverResidual, self.tdvp_error
+
+    def _solve_materialised(self, Eloc, gradients, logProbs, solve=True):
+        E = _kernels.as_dev(Eloc).reshape(-1)
+        lp = _kernels.as_dev(logProbs).reshape(-1)
+        G = _kernels.as_dev(gradients)
+        P = G.shape[-1]
+        G = G.reshape(-1, P)
+        n = E.shape[0]
+        N = mpi.globNumSamples if mpi.globNumSamples else n * mpi.comm.Get_size()
+        Pp = _kernels.round_up(P, 128)
+        self._buffers(P, Pp).zero_()
+        n_pad = _kernels.round_up(max(n, 1), 16)
+        O = _kernels.zeros(n_pad, Pp)
+        O[:n, :P] = G
+        first = _kernels.zeros(4 + Pp)
+        self._pass1_chunk(E, lp, O, n, Pp, first)
+        mpi.allreduce_(first)
+        self._set_first(first, N, P)
+        scratch = (_kernels.zeros(n_pad), _kernels.zeros(n_pad), _kernels.zeros(n_pad))
+        self._pass2_chunk(E, lp, O, n, n_pad, Pp, Pp, (first[4:] / N).contiguous(), float(first[0]) / N, scratch)
+        return self._finish(P, Pp, N, first)
+
+    def _set_first(self, first, N, P):
+        self.ElocMean = first[0] / N         # tdvp.py:37
+        self.ElocMeanAbs = first[1] / N      # tdvp.py:38
+        self._gradMean = first[4:4 + P] / N  # tdvp.py:41
+
+    # ---- the right-hand side ---------------------------------------------------------------------------
+    def __call__(self, netParameters, t, psi, evolutionEq, **rhsArgs):
+        nSamplesTDVP = rhsArgs["nSamplesTDVP"]
+        nSamplesObs = rhsArgs["nSamplesObs"]
+        mpi.globNumSamples = nSamplesTDVP
+        psi.set_parameters(netParameters)     # tdvp.py:100-101 (psi is left at the trial parameters, as in the reference)
+        timings = rhsArgs["timings"]
+        acc = {}
+
+        def tic():
+            if timings is not None:
+                torch.cuda.synchronize()
+                return time.perf_counter()
+            return 0.0
+
+        def toc(name, t0):
+            if timings is not None:
+                torch.cuda.synchronize()
+                acc[name] = acc.get(name, 0.0) + time.perf_counter() - t0
+
+        fused = hasattr(psi, "sample_range") and hasattr(evolutionEq, "equation_struct")
+        if not fused:  # duck-typed psi / evolutionEq: the reference's materialised flow (tdvp.py:116-127)
+            t0 = tic(); sampleConfigs, logProbs = psi.sample(numSamples=nSamplesTDVP); toc("sampling", t0)
+            t0 = tic(); Eloc, sampleGradients, logProbs = evolutionEq(psi, sampleConfigs, t); toc("compute Eloc", t0)
+            t0 = tic(); update, self.solverResidual, self.tdvp_error = self.solve(Eloc, sampleGradients, logProbs); toc("solve TDVP eqn.", t0)
+            x_all, lp_all, E_all = sampleConfigs.reshape(-1, sampleConfigs.shape[-1]), logProbs.reshape(-1), Eloc.reshape(-1)
+        else:
+            update, x_all, lp_all, E_all = self._fused_rhs(psi, evolutionEq, t, nSamplesTDVP, tic, toc)
+
+        if nSamplesObs > nSamplesTDVP:  # tdvp.py:130-134
+            t0 = tic()
+            xo, lpo = psi.sample(numSamples=nSamplesObs)
+            x_obs, lp_obs = xo.reshape(-1, xo.shape[-1]), lpo.reshape(-1)
+            n_obs_glob = nSamplesObs
+            toc("sampling observables", t0)
+        else:
+            x_obs, lp_obs, n_obs_glob = x_all, lp_all, nSamplesTDVP
+
+        if timings is not None:
+            for k, v in acc.items():
+                timings.timing_dict.setdefault(k, []).append(v)
+
+        if bool(torch.isnan(update).any()):  # tdvp.py:136-141
+            print(self.S0)
+            print(self.F0)
+            print("nan encountered. Exitting.")
+            raise SystemExit(1)
+
+        info = self._observables(psi, x_obs, lp_obs, E_all, n_obs_glob, nSamplesObs)
+        return update, info
+
+    def _plan_chunks(self, n_local, Pp):
+        """Rows of the O buffer and whether the whole local O fits (then local terms are evaluated once)."""
+        free, _ = torch.cuda.mem_get_info(global_defs.device())
+        fixed = 8 * Pp * Pp * 8 + (64 << 20)  # S0, SExp, CEO, shifted S, work copy, VT, eigh scratch (2)
+        budget = max(int((free - fixed) * self.memoryFraction), 16 * Pp * 8)
+        rows = self.chunkSamples if self.chunkSamples else budget // (Pp * 8)
+        rows = max(16, rows // 16 * 16)
+        n_pad = _kernels.round_up(max(n_local, 1), 16)
+        if rows >= n_pad:
+            return n_pad, True
+        return rows, False
+
+    def _fused_rhs(self, psi, evolutionEq, t, N, tic, toc):
+        h = psi.net.handle
+        P, Pp, d = h.P, h.Pp, h.dim
+        first_idx, n_local = mpi.shard_range(N)
+        key = psi.sampler.next_key()                       # sampler.py:73 (one key per psi.sample call)
+        chi2_all = psi.chi2_draws(n_local)
+        eq = evolutionEq.equation_struct(t)
+        self._buffers(P, Pp).zero_()
+        rows, stored = self._plan_chunks(n_local, Pp)
+        if getattr(self, "_Obuf", None) is None or self._Obuf.shape != (rows, Pp):
+            self._Obuf = None
+            self._Obuf = _kernels.zeros(rows, Pp)
+            self._scratch = (_kernels.zeros(rows), _kernels.zeros(rows), _kernels.zeros(rows))
+        O = self._Obuf
+        x_all, lp_all, E_all = _kernels.empty(n_local, d), _kernels.empty(n_local), _kernels.empty(n_local)
+        first = _kernels.zeros(4 + Pp)
+        chunks = [(c0, min(rows, n_local - c0)) for c0 in range(0, n_local, rows)] or [(0, 0)]
+
+        def local_chunk(c0, cn, sample):
+            if sample:
+                t0 = tic()
+                chi2 = chi2_all[c0:c0 + cn] if chi2_all is not None else None
+                x, lps = psi.sample_range(key, first_idx + c0, cn, N, chi2)
+                x_all[c0:c0 + cn] = x
+                toc("sampling", t0)
+            t0 = tic()
+            out = _kernels.local_terms(h, psi._flat, x_all[c0:c0 + cn], eq, O=O, ldo=Pp, want=("eloc", "logp"))
+            E_all[c0:c0 + cn] = out["eloc"]; lp_all[c0:c0 + cn] = out["logp"]
+            toc("compute Eloc", t0)
+            self.gpu_launches += 2 if sample else 1
+
+        # pass 1: samples, local terms, first moments (tdvp.py:117-122,37-41)
+        for c0, cn in chunks:
+            if cn == 0:
+                continue
+            local_chunk(c0, cn, True)
+            t0 = tic()
+            self._pass1_chunk(E_all[c0:c0 + cn], lp_all[c0:c0 + cn], O, cn, Pp, first)
+            toc("solve TDVP eqn.", t0)
+        t0 = tic()
+        mpi.allreduce_(first)
+        self._set_first(first, N, P)
+        meanO = (first[4:] / N).contiguous()
+        meanE = float(first[0]) / N
+        toc("solve TDVP eqn.", t0)
+        # pass 2: centring, force vector, weighted Grams (tdvp.py:40-47); local terms are re-evaluated chunk by chunk
+        # when the whole O does not fit in memory (same key and counters -> identical samples)
+        for c0, cn in chunks:
+            if cn == 0:
+                continue
+            if not stored:
+                local_chunk(c0, cn, False)
+            t0 = tic()
+            self._pass2_chunk(E_all[c0:c0 + cn], lp_all[c0:c0 + cn], O, cn, _kernels.round_up(cn, 16), Pp, Pp, meanO, meanE,
+                              self._scratch)
+            toc("solve TDVP eqn.", t0)
+        t0 = tic()
+        update = self._finish(P, Pp, N, first)
+        toc("solve TDVP eqn.", t0)
+        return update, x_all, lp_all, E_all
+
+    def _observables(self, psi, x, lp, E_all, n_glob, nSamplesObs):
+        """tdvp.py:143-162.  With several ranks the sums are all-reduced (the reference uses rank-local means)."""
+        d = x.shape[1]
+        n = x.shape[0]
+        ws = _kernels.obs_workspace(d)
+        first = _kernels.zeros(d + 2)
+        first[d + 1] = -float("inf")
+        same = E_all.shape[0] == n
+        _kernels.obs_first(x, lp, E_all if same else None, n, d, first, ws)
+        if same:
+            mx = first[d + 1].clone()
+        else:  # observables were re-sampled: max E_loc still refers to the TDVP samples (tdvp.py:150)
+            tmp = _kernels.zeros(3)
+            tmp[2] = -float("inf")
+            _kernels.obs_first(E_all.reshape(-1, 1), None, E_all, E_all.shape[0], 1, tmp, ws)
+            mx = tmp[2].clone()
+        mpi.allreduce_(first[:d + 1])
+        mean = (first[:d] / n_glob).contiguous()
+        central = _kernels.zeros(d * d + 4 * d)
+        _kernels.obs_central(x, n, d, mean, central, ws)
+        mpi.allreduce_(central)
+        central = central / n_glob
+        info = {}
+        info["x1"] = mean
+        info["covar"] = central[:d * d].view(d, d)
+        info["entropy"] = -first[d] / n_glob
+        for i, m in enumerate([3, 4, 5, 6]):
+            info[f"x{m}"] = central[d * d + i * d:d * d + (i + 1) * d]
+        if mpi.comm.Get_size() > 1:
+            import torch.distributed as dist
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        info["max_grad"] = mx
+        # integrate on small cells (tdvp.py:152-162): both draws use psi.sampler.key itself
+        first_idx, n_loc = mpi.shard_range(nSamplesObs)
+        key = psi.sampler.key
+        sums = _kernels.zeros(3)
+        lims = [1, 0.5, 0.1]
+        T = 10
+        for j, lim_normal in enumerate(lims):
+            lim = lim_normal * math.sqrt(T)
+            pts = _kernels.ball_points(key, first_idx, n_loc, nSamplesObs, d, lim)
+            lpb = psi(pts[None, ...])[0] if not hasattr(psi, "net") else _kernels.logp(psi.net.handle, psi._flat, pts)
+            _kernels.sum_exp(lpb, n_loc, sums[j:j + 1], ws)
+        mpi.allreduce_(sums)
+        for j, lim_normal in enumerate(lims):
+            lim = lim_normal * math.sqrt(T)
+            sphere_volume = math.pi ** (d / 2) / scipy.special.gamma(d / 2 + 1) * lim ** d
+            info[f"integral_{lim_normal}sigma"] = sums[j] / nSamplesObs * sphere_volume
+        self.gpu_launches += 12
+        return info
