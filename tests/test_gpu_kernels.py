@@ -1,0 +1,259 @@
+"""GPU parity tests, kernel level: every call goes through the C-ABI (libvmcpde.so) and is checked against the CPU
+oracle on the same seeded inputs.  Tolerances: float64 round-off, relative 1e-11 unless stated (the reference path is
+float64, main.py:2); RNG bits are exact, normals within a few ulp of scipy's erfinv."""
+import ctypes as C
+import os
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import flow, tdvp, threefry
+
+
+@pytest.fixture(scope="module")
+def L():
+    from vmc_pde_b200 import _lib
+    _lib.require_cuda()
+    return _lib.load()
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def relerr(a, b):
+    a = np.asarray(a.detach().cpu() if isinstance(a, torch.Tensor) else a)
+    b = np.asarray(b.detach().cpu() if isinstance(b, torch.Tensor) else b)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-300))
+
+
+CASES = [(2, 4, 1, "no_add", "Gauss", "diffusion", 1000),
+         (2, 3, 6, "no_add", "Gauss", "advection_paper", 333),
+         (6, 3, 5, "different_add", "Gauss", "advection_hamiltonian_wDiss", 777),
+         (8, 4, 4, "no_add", "Student_t", "diffusion", 2048),
+         (4, 2, 3, "add_s", "Gauss", "diffusion_anisotropic", 515),
+         (4, 2, 3, "jac_eq_1", "Student_t", "advection_hamiltonian", 100),
+         (10, 2, 20, "no_add", "Gauss", "diffusion_drift", 300),
+         (12, 1, 6, "no_add", "Gauss", "diffusion_anisotropic", 64),
+         (3, 2, 3, "no_add", "Gauss", "diffusion", 50),
+         (5, 2, 4, "different_add", "Gauss", "diffusion_drift", 50),
+         (2, 12, 2, "no_add", "Gauss", "diffusion", 40),
+         (6, 0, 1, "no_add", "Gauss", "diffusion", 40)]
+
+
+@pytest.mark.parametrize("d,depth,h,variant,latent,eqname,n", CASES)
+def test_sampler_local_terms_moments_gram(L, d, depth, h, variant, latent, eqname, n):
+    from vmc_pde_b200 import _lib, _capi
+    rng = np.random.default_rng(d * 1000 + depth * 10 + n)
+    ups, downs, _ = flow.make_index_splits(d, depth, 1)
+    off = rng.normal(size=d) * 0.3
+    spec = flow.FlowSpec(dim=d, depth=depth, hidden=(h,), latent=latent, variant=variant, offset=off, inds_up=ups, inds_down=downs)
+    th = flow.init_params(spec, 1) + 0.05 * rng.normal(size=spec.num_params)
+    st = flow.OracleState(spec, th)
+    cfg, keep = _capi.make_flow_config(d, depth, (h,), variant, latent, ups, downs, off)
+    fh = C.c_void_p()
+    _lib.check(L.vmcpde_flow_create(C.byref(cfg), C.byref(fh)))
+    P = L.vmcpde_flow_num_params(fh)
+    assert P == spec.num_params
+    Pp = L.vmcpde_padded_params(P)
+    f64 = torch.float64
+    tht = torch.tensor(th, device=dev())
+    # ---- sampler: bit-exact counters, same latent draw, same flow inverse
+    x = torch.empty(n, d, device=dev(), dtype=f64); lp = torch.empty(n, device=dev(), dtype=f64); z = torch.empty_like(x)
+    chi2 = None
+    if latent == "Student_t":
+        chi2_np = np.random.default_rng(5).chisquare(float(np.exp(th[spec.slices()[0]["dist_params"][0]]) + 1), size=n)
+        chi2 = torch.tensor(chi2_np, device=dev()); st.chi2 = lambda nu, m: chi2_np
+    key = threefry.split(st.key, 2)[1]
+    _lib.check(L.vmcpde_sample(fh, _lib.ptr(tht), int(key[0]), int(key[1]), 0, n, n, _lib.ptr(chi2), _lib.ptr(x), _lib.ptr(lp), _lib.ptr(z), _lib.stream()))
+    xo, lpo, zo = st.sample(n)
+    assert relerr(z, zo) < 1e-13 and relerr(x, xo) < 1e-12 and relerr(lp, lpo) < 1e-12
+    # a shard of the same stream reproduces the corresponding slice exactly
+    a, m = n // 3, n // 2
+    xs = torch.empty(m, d, device=dev(), dtype=f64); lps = torch.empty(m, device=dev(), dtype=f64)
+    _lib.check(L.vmcpde_sample(fh, _lib.ptr(tht), int(key[0]), int(key[1]), a, m, n, _lib.ptr(chi2[a:a + m].contiguous() if chi2 is not None else None),
+                               _lib.ptr(xs), _lib.ptr(lps), None, _lib.stream()))
+    assert torch.equal(xs, x[a:a + m]) and torch.equal(lps, lp[a:a + m])
+    # ---- fused local terms on the oracle's samples
+    xin = torch.tensor(xo.numpy(), device=dev())
+    A = torch.tensor(tdvp.random_D_factor(d), device=dev()) if eqname == "diffusion_anisotropic" else None
+    eq = _capi.make_equation(eqname, dict(tdvp.EQ_PARAMS.get(eqname, {})), 0.3, A.data_ptr() if A is not None else None)
+    nrow = (n + 15) // 16 * 16
+    E = torch.empty(n, device=dev(), dtype=f64); lp2 = torch.empty_like(E); g = torch.empty(n, d, device=dev(), dtype=f64); lap = torch.empty_like(E)
+    O = torch.full((nrow, Pp), float("nan"), device=dev(), dtype=f64)
+    O[n:] = 0
+    _lib.check(L.vmcpde_local_terms(fh, _lib.ptr(tht), _lib.ptr(xin), n, C.byref(eq), _lib.ptr(E), _lib.ptr(lp2), _lib.ptr(g), _lib.ptr(lap), _lib.ptr(O), Pp, _lib.stream()))
+    Eo, Oo, lpo2, go = tdvp.local_terms(st, xo, eqname, 0.3)
+    assert relerr(E, Eo) < 1e-11 and relerr(O[:n, :P], Oo) < 1e-11 and relerr(lp2, lpo2) < 1e-12
+    assert not torch.isnan(O).any() and (Pp == P or float(O[:, P:].abs().max()) == 0.0)   # every column written, padding zeroed
+    if eqname != "diffusion_anisotropic":
+        assert relerr(g, go) < 1e-11
+    lp3 = torch.empty_like(E)
+    _lib.check(L.vmcpde_logp(fh, _lib.ptr(tht), _lib.ptr(xin), n, _lib.ptr(lp3), _lib.stream()))
+    assert relerr(lp3, lpo2) < 1e-12
+    nh = min(n, 48)
+    H = torch.empty(nh, d, d, device=dev(), dtype=f64)
+    _lib.check(L.vmcpde_hessian(fh, _lib.ptr(tht), _lib.ptr(xin), nh, _lib.ptr(H), _lib.stream()))
+    assert relerr(H, st.hessian(xo[:nh])) < 1e-10
+    # flow transform round trip (main.py:77-96)
+    y = torch.empty_like(xin); lj = torch.empty_like(E); xb = torch.empty_like(xin); lji = torch.empty_like(E)
+    _lib.check(L.vmcpde_flow_transform(fh, _lib.ptr(tht), _lib.ptr(xin), n, 0, _lib.ptr(y), _lib.ptr(lj), None, _lib.stream()))
+    _lib.check(L.vmcpde_flow_transform(fh, _lib.ptr(tht), _lib.ptr(y), n, 1, _lib.ptr(xb), _lib.ptr(lji), None, _lib.stream()))
+    assert relerr(xb, xin) < 1e-11 and float((lj + lji).abs().max()) < 1e-10
+    # ---- first moments, centring, force, three weighted Grams (tdvp.py:36-52, 68-70)
+    T = tdvp.OracleTDVP(); T.solve(Eo.numpy(), Oo.numpy(), lpo2.numpy())
+    sums = torch.zeros(4 + Pp, device=dev(), dtype=f64)
+    _lib.check(L.vmcpde_moments1(_lib.ptr(E), _lib.ptr(lp2), _lib.ptr(O), n, Pp, _lib.ptr(sums), _lib.stream()))
+    assert abs(float(sums[0]) / n - T.ElocMean) <= 1e-11 * (abs(T.ElocMean) + np.abs(Eo.numpy()).max())
+    assert abs(float(sums[1]) / n - T.ElocMeanAbs) <= 1e-11 * T.ElocMeanAbs
+    assert relerr(sums[4:4 + P] / n, T.gradMean) < 1e-10
+    meanO = (sums[4:] / n).contiguous()
+    dE = torch.zeros(nrow, device=dev(), dtype=f64); wE = torch.zeros_like(dE); wLp = torch.zeros_like(dE)
+    F = torch.zeros(Pp, device=dev(), dtype=f64); var = torch.zeros(1, device=dev(), dtype=f64)
+    _lib.check(L.vmcpde_center_force(_lib.ptr(O), n, Pp, _lib.ptr(meanO), _lib.ptr(E), _lib.ptr(lp2), float(sums[0]) / n, _lib.ptr(dE), _lib.ptr(wE), _lib.ptr(wLp), _lib.ptr(F), _lib.ptr(var), _lib.stream()))
+    assert relerr(F[:P] / n, T.F0) < 1e-10 and abs(float(var) / n / T.ElocVar - 1) < 1e-11
+    S = [torch.zeros(Pp, Pp, device=dev(), dtype=f64) for _ in range(3)]
+    _lib.check(L.vmcpde_gram(_lib.ptr(O), nrow, Pp, Pp, 3, _lib.ptr_array([None, wLp, wE]), _lib.ptr_array(S), _lib.stream()))
+    for s_ in S:
+        _lib.check(L.vmcpde_sym_finalize(_lib.ptr(s_), Pp, 1.0 / n, _lib.stream()))
+    dO = Oo.numpy() - T.gradMean; dEo = Eo.numpy() - T.ElocMean
+    Ceo = (dO * (dEo ** 2)[:, None]).T @ dO / n
+    assert relerr(S[0][:P, :P], T.S0) < 1e-11 and relerr(S[1][:P, :P], T.SExp) < 1e-11 and relerr(S[2][:P, :P], Ceo) < 1e-11
+    assert float((S[0] - S[0].T).abs().max()) == 0.0
+    L.vmcpde_flow_destroy(fh)
+
+
+def test_rng_streams_bit_exact_and_golden(L):
+    from vmc_pde_b200 import _lib
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "rng.npz"))
+    k = threefry.prng_key(0)
+    u = torch.empty(64, device=dev(), dtype=torch.float64); nrm = torch.empty_like(u)
+    _lib.check(L.vmcpde_uniform(int(k[0]), int(k[1]), 0, 64, 64, _lib.ptr(u), _lib.stream()))
+    _lib.check(L.vmcpde_normal(int(k[0]), int(k[1]), 0, 64, 64, _lib.ptr(nrm), _lib.stream()))
+    assert np.array_equal(u.cpu().numpy(), g["uniform64"])                       # integer path + mantissa trick: exact
+    assert np.allclose(nrm.cpu().numpy(), g["normal64"], rtol=1e-14, atol=1e-15)  # erfinv: a few ulp
+    # offsets into a longer stream
+    k2 = threefry.prng_key(7)
+    part = torch.empty(100, device=dev(), dtype=torch.float64)
+    _lib.check(L.vmcpde_uniform(int(k2[0]), int(k2[1]), 900, 100, 5000, _lib.ptr(part), _lib.stream()))
+    assert np.array_equal(part.cpu().numpy(), threefry.uniform(k2, 5000)[900:1000])
+    # range validation
+    assert L.vmcpde_uniform(0, 0, 10, 100, 50, _lib.ptr(part), _lib.stream()) != 0
+    assert L.vmcpde_normal(0, 0, 0, 1, 2 ** 31 + 1, _lib.ptr(part), _lib.stream()) != 0  # 32-bit counter range
+
+
+def test_gram_properties_large(L):
+    """Size-independent properties at a BASELINE-sized panel (P = 8192): agreement with an independent FP64 product on a
+    slab, symmetry, linearity in the row weights, additivity over sample chunks, empty input."""
+    from vmc_pde_b200 import _lib
+    n, Pp = 4096, 8192
+    f64 = torch.float64
+    O = torch.randn(n, Pp, device=dev(), dtype=f64)
+    w = torch.rand(n, device=dev(), dtype=f64)
+    S = [torch.zeros(Pp, Pp, device=dev(), dtype=f64) for _ in range(2)]
+    _lib.check(L.vmcpde_gram(_lib.ptr(O), n, Pp, Pp, 2, _lib.ptr_array([None, w]), _lib.ptr_array(S), _lib.stream()))
+    ref = O[:, 1000:1256].T @ O
+    refw = (O[:, 1000:1256] * w[:, None]).T @ O
+    up = torch.triu(torch.ones(Pp, Pp, device=dev(), dtype=torch.bool))[1000:1256]
+    assert float(((S[0][1000:1256] - ref) * up).abs().max()) < 1e-10 * float(ref.abs().max())
+    assert float(((S[1][1000:1256] - refw) * up).abs().max()) < 1e-10 * float(refw.abs().max())
+    # two chunks accumulate to the same result; doubling the weights doubles the matrix
+    S2 = torch.zeros(Pp, Pp, device=dev(), dtype=f64)
+    w2 = (2 * w).contiguous()
+    for c0 in (0, n // 2):
+        _lib.check(L.vmcpde_gram(_lib.ptr(O[c0:c0 + n // 2]), n // 2, Pp, Pp, 1, _lib.ptr_array([w2[c0:c0 + n // 2]]), _lib.ptr_array([S2]), _lib.stream()))
+    assert float((torch.triu(S2) - 2 * torch.triu(S[1])).abs().max()) < 1e-9 * float(S[1].abs().max())
+    before = S2.clone()
+    _lib.check(L.vmcpde_gram(_lib.ptr(O), 0, Pp, Pp, 1, _lib.ptr_array([None]), _lib.ptr_array([S2]), _lib.stream()))
+    assert torch.equal(before, S2)
+    assert L.vmcpde_gram(_lib.ptr(O), 17, Pp, Pp, 1, _lib.ptr_array([None]), _lib.ptr_array([S2]), _lib.stream()) != 0  # n % 16
+    _lib.check(L.vmcpde_sym_finalize(_lib.ptr(S[0]), Pp, 1.0, _lib.stream()))
+    assert torch.equal(S[0], S[0].T)
+
+
+def test_gemm_tn(L):
+    from vmc_pde_b200 import _lib
+    K, M, N = 528, 256, 384
+    X = torch.randn(K, M, device=dev(), dtype=torch.float64); Y = torch.randn(K, N, device=dev(), dtype=torch.float64)
+    Out = torch.randn(M, N, device=dev(), dtype=torch.float64)
+    ref = 0.5 * X.T @ Y + 2.0 * Out
+    _lib.check(L.vmcpde_gemm_tn(_lib.ptr(X), M, _lib.ptr(Y), N, _lib.ptr(Out), N, M, N, K, 0.5, 2.0, _lib.stream()))
+    assert relerr(Out, ref) < 1e-13
+
+
+def _eigh(L, S_np):
+    from vmc_pde_b200 import _lib
+    n = S_np.shape[0]; ld = L.vmcpde_padded_params(n)
+    S = torch.zeros(ld, ld, device=dev(), dtype=torch.float64); S[:n, :n] = torch.tensor(S_np, device=dev())
+    ev = torch.zeros(ld, device=dev(), dtype=torch.float64); VT = torch.zeros(ld, ld, device=dev(), dtype=torch.float64)
+    nb = C.c_size_t(0); _lib.check(L.vmcpde_eigh_workspace_bytes(n, ld, C.byref(nb)))
+    ws = torch.empty(nb.value, device=dev(), dtype=torch.uint8)
+    _lib.check(L.vmcpde_eigh(_lib.ptr(S), n, ld, _lib.ptr(ev), _lib.ptr(VT), _lib.ptr(ws), nb.value, _lib.stream()))
+    return ev[:n].cpu().numpy(), VT[:n, :n].cpu().numpy().T
+
+
+def test_eigh_against_lapack(L):
+    rng = np.random.default_rng(0)
+    mats = []
+    for n in (1, 2, 3, 37, 130, 300, 1000):
+        A = rng.normal(size=(n, n)); mats.append((A + A.T) / 2)
+    A = rng.normal(size=(3000, 200)) @ rng.normal(size=(200, 600)); mats.append(A.T @ A / 3000)        # rank deficient
+    cs = 10.0 ** (-6.0 * np.arange(1100) / 1100); A = rng.normal(size=(3000, 1100)) * cs; mats.append(A.T @ A / 3000)  # graded
+    mats.append(np.diag(rng.normal(size=50)))                                                          # already diagonal
+    mats.append(np.zeros((20, 20)))
+    for S in mats:
+        n = S.shape[0]
+        ev, V = _eigh(L, S)
+        ref = np.linalg.eigvalsh(S); nrm = max(np.abs(ref).max(), 1e-300)
+        assert np.all(np.diff(ev) >= 0)
+        assert np.abs(ev - ref).max() <= 1e-13 * nrm + 1e-300
+        assert np.abs(S @ V - V * ev).max() <= 2e-13 * nrm + 1e-300
+        assert np.abs(V.T @ V - np.eye(n)).max() < 1e-12
+
+
+def test_solve_tail_and_cholesky_against_oracle(L):
+    from vmc_pde_b200 import _lib
+    rng = np.random.default_rng(3)
+    f64 = torch.float64
+    for (n, Ns, useSNR) in ((37, 2000, 0), (300, 4000, 1)):
+        ld = L.vmcpde_padded_params(n)
+        O_ = rng.normal(size=(Ns, n)) * 10.0 ** (-3.0 * np.arange(n) / n)
+        O_[:, n // 2:] = O_[:, : n - n // 2] @ rng.normal(size=(n - n // 2, n - n // 2)) * 1e-1   # exactly rank deficient
+        E = rng.normal(size=Ns) + 0.3; lp = rng.normal(size=Ns)
+        T = tdvp.OracleTDVP(useSNR=bool(useSNR)); upd = T.solve(E, O_, lp)
+        dO = O_ - O_.mean(0); dE = E - E.mean(); CEO = (dO * (dE ** 2)[:, None]).T @ dO / Ns
+        def Pd(a):
+            t = torch.zeros(ld, ld, device=dev(), dtype=f64); t[:n, :n] = torch.tensor(a, device=dev()); return t
+        S, S0, Cg = Pd(T.S), Pd(T.S0), Pd(CEO)
+        F = torch.zeros(ld, device=dev(), dtype=f64); F[:n] = torch.tensor(T.F0, device=dev())
+        ev = torch.zeros(ld, device=dev(), dtype=f64); VT = torch.zeros(ld, ld, device=dev(), dtype=f64)
+        a, b = C.c_size_t(0), C.c_size_t(0)
+        L.vmcpde_eigh_workspace_bytes(n, ld, C.byref(a)); L.vmcpde_solve_tail_workspace_bytes(n, ld, C.byref(b))
+        ws = torch.empty(max(a.value, b.value), device=dev(), dtype=torch.uint8)
+        A = S.clone()
+        _lib.check(L.vmcpde_eigh(_lib.ptr(A), n, ld, _lib.ptr(ev), _lib.ptr(VT), _lib.ptr(ws), ws.numel(), _lib.stream()))
+        outs = [torch.zeros(ld, device=dev(), dtype=f64) for _ in range(5)]; sc = torch.zeros(2, device=dev(), dtype=f64)
+        _lib.check(L.vmcpde_solve_tail(_lib.ptr(ev), _lib.ptr(VT), n, ld, _lib.ptr(F), _lib.ptr(S), _lib.ptr(S0), _lib.ptr(Cg), float(Ns), 1e-11, 2.0, useSNR,
+                                       float(np.mean(E ** 2)), *[_lib.ptr(o) for o in outs], _lib.ptr(sc), _lib.ptr(ws), ws.numel(), _lib.stream()))
+        VtF, rhoVar, snr, invEv, update = [o[:n].cpu().numpy() for o in outs]
+        du = update - upd
+        # theta_dot is compared in the S-norm: null-space components are undefined
+        assert du @ T.S0 @ du <= 1e-16 * (upd @ T.S0 @ upd)
+        assert relerr(ev[:n], T.ev) < 1e-13
+        assert abs(float(sc[1]) - T.tdvp_error) < 1e-11 and float(sc[0]) < 10 * T.solverResidual + 1e-12
+        big = np.abs(T.ev / T.ev[-1]) > 1e-8
+        assert np.abs(snr[big] / T.snr[big] - 1).max() < 1e-6 and relerr(rhoVar[big], T.rhoVar[big]) < 1e-9
+        assert np.array_equal(invEv == 0, T.invEv == 0)
+    for n in (5, 64, 65, 300, 1000):
+        ld = L.vmcpde_padded_params(n); A = rng.normal(size=(n + 50, n)); Sn = A.T @ A / n + 1e-3 * np.eye(n); Fn = rng.normal(size=n)
+        S = torch.zeros(ld, ld, device=dev(), dtype=f64); S[:n, :n] = torch.tensor(Sn, device=dev()); F = torch.tensor(Fn, device=dev())
+        x = torch.zeros(n, device=dev(), dtype=f64); info = torch.zeros(1, device=dev(), dtype=torch.int32)
+        _lib.check(L.vmcpde_chol_solve(_lib.ptr(S), n, ld, _lib.ptr(F), _lib.ptr(x), _lib.ptr(info), _lib.stream()))
+        assert int(info) == 0 and relerr(x, np.linalg.solve(Sn, Fn)) < 1e-10
+    # a singular matrix is reported, not silently "solved"
+    S = torch.zeros(128, 128, device=dev(), dtype=f64); S[:4, :4] = torch.tensor(np.ones((4, 4)), device=dev())
+    info = torch.zeros(1, device=dev(), dtype=torch.int32); x = torch.zeros(4, device=dev(), dtype=f64)
+    _lib.check(L.vmcpde_chol_solve(_lib.ptr(S), 4, 128, _lib.ptr(torch.ones(4, device=dev(), dtype=f64)), _lib.ptr(x), _lib.ptr(info), _lib.stream()))
+    assert int(info) == 2

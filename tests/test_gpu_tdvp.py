@@ -1,0 +1,236 @@
+"""GPU parity tests through the reference-mirroring Python surface (sampler / var_state / evolutionEq / tdvp / stepper),
+written the way main.py drives the reference (main.py:69-73,113-118,159-162), checked against the CPU oracle."""
+import os
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import flow as oflow, tdvp as otdvp
+
+
+def relerr(a, b):
+    a = np.asarray(a.detach().cpu() if isinstance(a, torch.Tensor) else a)
+    b = np.asarray(b.detach().cpu() if isinstance(b, torch.Tensor) else b)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-300))
+
+
+def norm_fun(v, S):  # main.py:24-26
+    return v @ S @ v
+
+
+def build(d, depth, h, variant, latent, eqname, offset):
+    from vmc_pde_b200 import sampler, var_state, evolutionEq, net
+    smp = sampler.Sampler(dim=d, numChains=30, name=latent, mcmc_info={"offset": offset, "bound": 0.25})
+    net.SingleBlock.different_add = (variant == "different_add")   # the reference selects variants by editing class defaults
+    try:
+        vs = var_state.VarState(smp, d, 1, depth, network_args={"intmediate": (h,), "offset": offset, "latentSpaceName": latent, "dim": d})
+    finally:
+        net.SingleBlock.different_add = False
+    eq = evolutionEq.EvolutionEquation(dim=d, name=eqname)
+    spec = oflow.FlowSpec(dim=d, depth=depth, hidden=(h,), latent=latent, variant=variant, offset=offset,
+                          inds_up=vs.net.inds_up, inds_down=vs.net.inds_down)
+    assert spec.num_params == vs.numParameters
+    return smp, vs, eq, spec
+
+
+RHS_CASES = [(2, 4, 1, "no_add", "Gauss", "diffusion", 10000, np.zeros(2)),                       # C1: main.py 'mwe'
+             (6, 4, 3, "different_add", "Gauss", "advection_hamiltonian_wDiss", 6000, np.array([1., 0, 0, 1, 0, 0])),  # 'harmonicOsc_diff', P = 411
+             (8, 4, 4, "no_add", "Gauss", "diffusion", 5000, np.zeros(8)),                        # P = 364
+             (4, 3, 6, "no_add", "Gauss", "diffusion_anisotropic", 3000, np.zeros(4)),
+             (2, 4, 2, "no_add", "Gauss", "advection_hamiltonian", 2000, np.ones(2))]              # 'harmonicOsc'
+
+
+@pytest.mark.parametrize("d,depth,h,variant,latent,eqname,N,offset", RHS_CASES)
+def test_tdvp_rhs_matches_oracle(d, depth, h, variant, latent, eqname, N, offset):
+    from vmc_pde_b200 import tdvp, util
+    smp, vs, eq, spec = build(d, depth, h, variant, latent, eqname, offset)
+    theta = vs.get_parameters()
+    th_np = theta.cpu().numpy()
+    assert np.array_equal(th_np[spec.slices()[0]["L_diag"][0]:spec.slices()[0]["mu"][1]], np.zeros(2 * d))  # latent params start at 0
+    ost = oflow.OracleState(spec, th_np)
+    OT = otdvp.OracleTDVP()
+    upd_o, info_o = OT.rhs(ost, th_np, eqname, N)
+    T = tdvp.TDVP()
+    tm = util.Timings()
+    upd, info = T(theta, 0.0, psi=vs, evolutionEq=eq, nSamplesTDVP=N, nSamplesObs=N, timings=tm)
+    assert set(tm.timing_dict) == {"sampling", "compute Eloc", "solve TDVP eqn."}              # tdvp.py:116-128
+    assert relerr(T.S0, OT.S0) < 1e-11 and relerr(T.SExp, OT.SExp) < 1e-11 and relerr(T.F0, OT.F0) < 1e-10
+    assert relerr(T.S, OT.S) < 1e-11 and relerr(T.ev, OT.ev) < 1e-12
+    du = upd.cpu().numpy() - upd_o
+    assert du @ OT.S0 @ du <= 1e-14 * (upd_o @ OT.S0 @ upd_o)                                   # theta_dot in the S-norm
+    assert abs(float(T.tdvp_error) - OT.tdvp_error) < 1e-10 and float(T.solverResidual) < 10 * OT.solverResidual + 1e-12
+    assert abs(float(T.ElocMean) - OT.ElocMean) < 1e-10 * (1 + abs(OT.ElocMean)) and abs(float(T.ElocVar) / OT.ElocVar - 1) < 1e-10
+    assert abs(float(T.ElocMeanAbs) / OT.ElocMeanAbs - 1) < 1e-10
+    V = T.V.cpu().numpy()
+    assert np.abs(V.T @ V - np.eye(V.shape[0])).max() < 1e-11
+    big = np.abs(OT.ev / OT.ev[-1]) > 1e-6
+    assert np.abs(T.snr.cpu().numpy()[big] / OT.snr[big] - 1).max() < 1e-5
+    for k in ("x1", "covar", "entropy", "x3", "x4", "x5", "x6", "max_grad", "integral_1sigma", "integral_0.5sigma", "integral_0.1sigma"):
+        assert relerr(info[k], info_o[k]) < 1e-10, k
+    # psi is left at the trial parameters and the sampler key advanced exactly once (tdvp.py:100-101; sampler.py:73)
+    assert torch.equal(vs.get_parameters(), theta) and np.array_equal(vs.sampler.key, ost.key)
+
+
+def test_kat_depth0_analytic_on_gpu():
+    """SURVEY KAT 1 through the CUDA path: zero blocks, Gauss, diffusion => d/dt L_diag = 1 exactly, full-rank S."""
+    from vmc_pde_b200 import tdvp
+    for d in (2, 6):
+        smp, vs, eq, spec = build(d, 0, 1, "no_add", "Gauss", "diffusion", np.zeros(d))
+        T = tdvp.TDVP()
+        upd, info = T(vs.get_parameters(), 0.0, psi=vs, evolutionEq=eq, nSamplesTDVP=20000, nSamplesObs=20000, timings=None)
+        u = upd.cpu().numpy()
+        a = d * (d - 1) // 2
+        assert np.allclose(u[a:a + d], 1.0, atol=1e-11) and np.abs(np.delete(u, np.arange(a, a + d))).max() < 1e-11
+        assert float(T.solverResidual) < 1e-12
+        assert abs(float(info["entropy"]) - 0.5 * d * np.log(2 * np.pi * np.e)) < 0.05   # visualization.py:188 at t = 0
+
+
+@pytest.mark.parametrize("name", ["c1_mwe", "phase_space", "student_t"])
+def test_golden_fixtures(name):
+    """Committed oracle outputs (tests/golden/make_golden.py): samples, local terms, S0, F0, update."""
+    from vmc_pde_b200 import tdvp, _kernels, mpi_wrapper
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    d, depth, h, n = int(g["dim"]), int(g["depth"]), int(g["hidden"]), int(g["n"])
+    smp, vs, eq, spec = build(d, depth, h, str(g["variant"]), str(g["latent"]), str(g["equation"]), g["offset"])
+    assert np.array_equal(np.asarray(vs.net.inds_up), g["inds_up"]) and np.array_equal(np.asarray(vs.net.inds_down), g["inds_down"])
+    vs.set_parameters(g["theta"])
+    assert np.array_equal(vs.sampler.key, g["sampler_key"])
+    key = vs.sampler.next_key()
+    chi2 = _kernels.as_dev(g["chi2"]) if g["chi2"].size else None
+    x, lp = vs.sample_range(key, 0, n, n, chi2)
+    assert relerr(x, g["x"]) < 1e-12 and relerr(lp, g["logp"]) < 1e-12
+    E, O, lp2 = eq(vs, torch.tensor(g["x"])[None, ...], float(g["t"]))
+    assert E.shape == (1, n) and O.shape == (1, n, vs.numParameters)
+    assert relerr(E, g["eloc"][None]) < 1e-11 and relerr(O[0, :8], g["O_head"]) < 1e-11
+    lp3, gx, O2 = vs(torch.tensor(g["x"])[None, ...], mode="eval_coordgrads")
+    assert relerr(gx[0], g["grad"]) < 1e-11 and relerr(lp3[0], g["logp"]) < 1e-12
+    assert relerr(vs(torch.tensor(g["x"])[None, ...]), g["logp"][None]) < 1e-12
+    mpi_wrapper.globNumSamples = n
+    T = tdvp.TDVP()
+    upd, res, terr = T.solve(E, O, lp2)
+    assert relerr(T.S0, g["S0"]) < 1e-11 and relerr(T.SExp, g["SExp"]) < 1e-11 and relerr(T.F0, g["F0"]) < 1e-10
+    du = upd.cpu().numpy() - g["update"]
+    assert du @ g["S0"] @ du <= 1e-13 * (g["update"] @ g["S0"] @ g["update"])
+    # eigenvalues sitting on the soft cut-off (|ev/ev_max| ~ svdTol) make the retained part of the solution sensitive to
+    # round-off in S at the 1e-9 level (regulariser ~ (r/svdTol)^6), hence the looser bound on this scalar
+    assert abs(float(terr) - float(g["tdvp_error"])) < 1e-7
+
+
+def test_steppers_and_chunked_two_pass_match_oracle():
+    from vmc_pde_b200 import tdvp, stepper
+    z2 = np.zeros(2)
+    smp, vs, eq, spec = build(2, 4, 1, "no_add", "Gauss", "diffusion", z2)
+    theta0 = vs.get_parameters(); th_np = theta0.cpu().numpy()
+    ost = oflow.OracleState(spec, th_np); OT = otdvp.OracleTDVP()
+    y_o, dt_o = otdvp.heun_step(lambda y, k: OT.rhs(ost, y, "diffusion", 4000, observables=False)[0], th_np, 1e-3, 1e-2, 1.3)
+    # chunkSamples forces the recompute-in-two-passes path (O never held for all samples)
+    T = tdvp.TDVP(chunkSamples=1024)
+    st = stepper.FixedStepper(timeStep=1e-3, mode='Heun', maxStep=1e-2, increase_fac=1.3)
+    y, dt, info = st.step(0, T, theta0, evolutionEq=eq, psi=vs, nSamplesTDVP=4000, nSamplesObs=4000, normFunction=norm_fun, timings=None, integrals=False)
+    assert abs(dt - dt_o) < 1e-18 and relerr(y, y_o) < 1e-10 and "entropy" in info
+    # the stored-O path gives the same step
+    smp, vs2, eq2, _ = build(2, 4, 1, "no_add", "Gauss", "diffusion", z2)
+    st2 = stepper.FixedStepper(timeStep=1e-3, mode='Heun', maxStep=1e-2, increase_fac=1.3)
+    y2, _, _ = st2.step(0, tdvp.TDVP(), theta0, evolutionEq=eq2, psi=vs2, nSamplesTDVP=4000, nSamplesObs=4000, normFunction=norm_fun, timings=None)
+    assert relerr(y2, y.cpu().numpy()) < 1e-11
+    # adaptive Heun: 5 RHS calls per attempt, error in the SExp quadratic form (stepper.py:54-72)
+    smp, vs3, eq3, spec3 = build(2, 4, 1, "no_add", "Gauss", "diffusion", z2)
+    ost = oflow.OracleState(spec3, th_np); OT = otdvp.OracleTDVP()
+    y_o, rdt_o, ndt_o = otdvp.adaptive_heun_step(lambda y, k: OT.rhs(ost, y, "diffusion", 3000, observables=False)[0], th_np, 1e-3, 1e-2, 1e-2,
+                                                 lambda v: v @ OT.SExp @ v)
+    ah = stepper.AdaptiveHeun(timeStep=1e-3, tol=1e-2, maxStep=1e-2)
+    y3, rdt, _ = ah.step(0, tdvp.TDVP(), theta0, evolutionEq=eq3, psi=vs3, nSamplesTDVP=3000, nSamplesObs=3000, normFunction=norm_fun, timings=None)
+    assert abs(rdt - rdt_o) < 1e-18 and abs(ah.dt - ndt_o) < 1e-15 and relerr(y3, y_o) < 1e-10
+
+
+def test_observable_resampling_and_student_t():
+    """nSamplesObs > nSamplesTDVP re-samples (tdvp.py:130-134); Student-t latent incl. the nu gradient and host chi^2."""
+    from vmc_pde_b200 import tdvp, util
+    smp, vs, eq, spec = build(4, 2, 3, "no_add", "Student_t", "diffusion", np.zeros(4))
+    theta = vs.get_parameters()
+    np.random.seed(11)
+    T = tdvp.TDVP()
+    tm = util.Timings()
+    upd, info = T(theta, 0.0, psi=vs, evolutionEq=eq, nSamplesTDVP=3000, nSamplesObs=5000, timings=tm)
+    assert "sampling observables" in tm.timing_dict
+    # oracle with the same chi^2 stream: NumPy's global RNG, consumed in the same order (sampler.py:32)
+    np.random.seed(11)
+    ost = oflow.OracleState(spec, theta.cpu().numpy())
+    ost.chi2 = lambda nu, m: np.random.chisquare(nu, size=(m,))
+    OT = otdvp.OracleTDVP()
+    upd_o, _ = OT.rhs(ost, theta.cpu().numpy(), "diffusion", 3000, observables=False)
+    du = upd.cpu().numpy() - upd_o
+    assert relerr(T.S0, OT.S0) < 1e-10 and du @ OT.S0 @ du <= 1e-12 * (upd_o @ OT.S0 @ upd_o)
+    xo, lpo, _ = ost.sample(5000)
+    assert abs(float(info["entropy"]) + float(lpo.mean())) < 1e-10 and relerr(info["x1"], xo.numpy().mean(0)) < 1e-9
+    assert torch.isfinite(upd).all() and float(T.ev[-1]) > 0
+
+
+def test_shifted_cholesky_extension_and_errors():
+    from vmc_pde_b200 import tdvp
+    smp, vs, eq, spec = build(6, 4, 3, "no_add", "Gauss", "diffusion", np.zeros(6))
+    theta0 = vs.get_parameters()
+    T2 = tdvp.TDVP(diagonalShift=1e-4, solver="cholesky")
+    u2, _ = T2(theta0, 0.0, psi=vs, evolutionEq=eq, nSamplesTDVP=4000, nSamplesObs=4000, timings=None)
+    S, F = T2.S.cpu().numpy(), T2.F0.cpu().numpy()
+    assert np.linalg.norm(S @ u2.cpu().numpy() - F) <= 1e-10 * np.linalg.norm(F) and float(T2.solverResidual) < 1e-10
+    assert np.allclose(np.diag(S), np.diag(T2.S0.cpu().numpy()) * (1 + 1e-4))                   # tdvp.py:50-51 multiplicative shift
+    assert T2.ev is None and T2.V is None
+    with pytest.raises(ValueError, match="diagonalShift"):
+        tdvp.TDVP(solver="cholesky")(theta0, 0.0, psi=vs, evolutionEq=eq, nSamplesTDVP=256, nSamplesObs=256, timings=None)
+    with pytest.raises(KeyError):
+        tdvp.TDVP()(theta0, 0.0, psi=vs, evolutionEq=eq, nSamplesTDVP=256, nSamplesObs=256)   # 'timings' is a required key (tdvp.py:103)
+    with pytest.raises(ValueError):
+        vs.set_parameters(torch.zeros(3))
+
+
+def test_driver_loop_like_main_py():
+    """main.py:159-190 in miniature: Heun steps on the 'mwe' mode; entropy follows 1/2 d log(2 pi e (1 + 2t))."""
+    from vmc_pde_b200 import tdvp, stepper, util
+    smp, vs, eq, spec = build(2, 4, 1, "no_add", "Gauss", "diffusion", np.zeros(2))
+    myStepper = stepper.FixedStepper(timeStep=1e-3, mode='Heun', maxStep=2e-2, increase_fac=1.5)
+    tdvpEq, timings = tdvp.TDVP(), util.Timings()
+    t, infos = 0.0, {"times": [], "ev": [], "snr": [], "solver_res": [], "tdvp_error": []}
+    for _ in range(12):
+        dp, dt, info = myStepper.step(0, tdvpEq, vs.get_parameters(), evolutionEq=eq, psi=vs, nSamplesTDVP=8000, nSamplesObs=8000,
+                                      normFunction=norm_fun, timings=timings, integrals=False)
+        vs.set_parameters(dp)
+        infos["times"].append(t); infos["ev"].append(tdvpEq.ev); infos["snr"].append(tdvpEq.snr)
+        infos["solver_res"].append(tdvpEq.solverResidual); infos["tdvp_error"].append(tdvpEq.tdvp_error)
+        t += dt
+    exact = 0.5 * 2 * np.log(2 * np.pi * np.e * (1 + 2 * (t - dt)))
+    assert abs(float(info["entropy"]) - exact) < 0.06
+    assert float(infos["tdvp_error"][-1]) < 5e-3 and float(infos["solver_res"][-1]) < 1e-6
+    assert abs(float(torch.diagonal(info["covar"]).mean()) - (1 + 2 * (t - dt))) < 0.08
+    x0, _ = vs.net.apply(vs.params, np.zeros(2), evaluate=False, inv=True)                     # main.py:202
+    assert x0.shape == (2,)
+
+
+def test_full_size_properties_c3():
+    """BASELINE configs[2] sizes (d=6, P=8187, N=2^18): properties that do not need the oracle at this size --
+    symmetric PSD Gram, S theta_dot = F on the retained spectrum, TDVP error in [0,1), Gram trace equals the sum of
+    per-parameter variances obtained from a direct evaluation of O on a sub-sample."""
+    from vmc_pde_b200 import tdvp, _kernels
+    smp, vs, eq, spec = build(6, 8, 36, "different_add", "Gauss", "advection_hamiltonian_wDiss", np.array([1., 0, 0, 1, 0, 0]))
+    assert vs.numParameters == 8187
+    N = 2 ** 18
+    T = tdvp.TDVP()
+    key_before = vs.sampler.key.copy()
+    upd, info = T(vs.get_parameters(), 0.0, psi=vs, evolutionEq=eq, nSamplesTDVP=N, nSamplesObs=N, timings=None)
+    assert torch.isfinite(upd).all()
+    assert torch.equal(T.S0, T.S0.T) and float(T.ev[0]) > -1e-10 * float(T.ev[-1])
+    assert abs(float(T.ev.sum()) / float(torch.diagonal(T.S0).sum()) - 1) < 1e-10            # trace is preserved by eigh
+    assert float(T.solverResidual) < 1e-6 and 0 <= float(T.tdvp_error) < 1
+    V = T.V
+    assert float((V[:, -50:].T @ V[:, -50:] - torch.eye(50, device=V.device, dtype=V.dtype)).abs().max()) < 1e-11
+    # independent check of diag(S0) and F on the first 4096 samples of the same stream (counter-based RNG)
+    from vmc_pde_b200 import _threefry
+    use = _threefry.split(key_before, 2)[1]
+    x, _ = vs.sample_range(use, 0, 4096, N)
+    E, O, lp = eq(vs, x[None, ...], 0.0)
+    var_sub = O[0].var(dim=0, unbiased=False)
+    ratio = (torch.diagonal(T.S0) / var_sub)[var_sub > 1e-12 * var_sub.max()]
+    assert 0.5 < float(ratio.median()) < 2.0
+    assert abs(float(info["entropy"]) - 0.5 * 6 * np.log(2 * np.pi * np.e)) < 0.05

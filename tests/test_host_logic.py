@@ -1,0 +1,112 @@
+"""CPU: host-side logic of the mirror modules (steppers, sharding arithmetic, reductions over gloo with 2 ranks)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from oracle import tdvp as otdvp
+from vmc_pde_b200 import stepper, mpi_wrapper, util
+
+
+class MockRHS:
+    """y' = A y with a fixed SExp, the interface stepper.py expects from TDVP (callable + .SExp)."""
+
+    def __init__(self, A):
+        self.A, self.SExp, self.calls = A, torch.eye(A.shape[0], dtype=torch.float64), []
+
+    def __call__(self, y, t, **kw):
+        self.calls.append(kw["intStep"])
+        return self.A @ y, {"k": kw["intStep"]}
+
+
+def test_fixed_stepper_matches_reference_semantics():
+    A = torch.tensor([[-1.0, 0.3], [0.0, -2.0]], dtype=torch.float64)
+    y0 = torch.tensor([1.0, 2.0], dtype=torch.float64)
+    f = MockRHS(A)
+    st = stepper.FixedStepper(timeStep=1e-2, mode='Heun', maxStep=1.0, increase_fac=1.3)
+    y, dt, info = st.step(0, f, y0, extra=1)
+    yo, dto = otdvp.heun_step(lambda y, k: A.numpy() @ y, y0.numpy(), 1e-2, 1.0, 1.3)
+    assert abs(dt - dto) < 1e-16 and np.allclose(y.numpy(), yo, atol=1e-15)
+    assert f.calls == [0, 1] and info == {"k": 1}          # stepper.py:135-137: info comes from the second call
+    assert torch.equal(y0, torch.tensor([1.0, 2.0], dtype=torch.float64))  # input untouched
+    st = stepper.FixedStepper(timeStep=1e-2, mode='Euler', maxStep=1.5e-2, increase_fac=2.0)
+    y, dt, _ = st.step(0, MockRHS(A), y0)
+    assert abs(dt - 1.5e-2) < 1e-16 and np.allclose(y.numpy(), (y0 + dt * (A @ y0)).numpy())
+
+
+def test_adaptive_heun_matches_reference_semantics():
+    A = torch.tensor([[-3.0, 0.5], [0.2, -1.0]], dtype=torch.float64)
+    y0 = torch.tensor([1.0, -1.0], dtype=torch.float64)
+    f = MockRHS(A)
+    norm = lambda v, S: v @ S @ v   # main.py:24-26 (a quadratic form, no square root)
+    ah = stepper.AdaptiveHeun(timeStep=0.2, tol=1e-6, maxStep=1.0)
+    y, rdt, info = ah.step(0, f, y0, normFunction=norm)
+    yo, rdto, ndto = otdvp.adaptive_heun_step(lambda y, k: A.numpy() @ y, y0.numpy(), 0.2, 1e-6, 1.0, lambda v: float(v @ v))
+    assert abs(rdt - rdto) < 1e-15 and abs(ah.dt - ndto) < 1e-15 and np.allclose(y.numpy(), yo, atol=1e-14)
+    assert len(f.calls) % 5 == 0 and f.calls[:5] == [0, 1, 2, 3, 4] and info == {"k": 0}
+
+
+def test_distribute_sampling_arithmetic():
+    """mpi_wrapper.py:68-126 on one process."""
+    assert mpi_wrapper.distribute_sampling(1000) == 1000 and mpi_wrapper.globNumSamples == 1000
+    assert mpi_wrapper.distribute_sampling(1000, localDevices=1, numChainsPerDevice=30) == 34
+    assert mpi_wrapper.globNumSamples == 34 * 30
+    assert mpi_wrapper.first_sample_id() == 0
+    assert mpi_wrapper.shard_range(10) == (0, 10)
+    assert mpi_wrapper.rank == 0 and mpi_wrapper.commSize == 1
+
+
+def test_timings_and_cov_matrix():
+    t = util.Timings()
+    t.start_timing("a"); t.stop_timing("a")
+    assert t.timing_dict["a"][-1] >= 0
+    S = util.build_cov_matrix(torch.tensor([0.5, -0.2, 0.1], dtype=torch.float64), torch.tensor([0.1, 0.0, -0.3], dtype=torch.float64), 3)
+    L = np.array([[np.exp(0.1), 0.5, -0.2], [0, 1.0, 0.1], [0, 0, np.exp(-0.3)]])
+    assert np.allclose(S.numpy(), L @ L.T)
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vmc_pde_b200 import mpi_wrapper as mpi
+    N = 11
+    first, n = mpi.shard_range(N)
+    rng = np.random.default_rng(0)
+    full = torch.tensor(rng.normal(size=(1, N, 3)))
+    mine = full[:, first:first + n]
+    mpi.globNumSamples = N
+    out = dict(rank=mpi.rank, size=mpi.commSize, first=first, n=n,
+               sum=mpi.global_sum(mine).numpy(), mean=mpi.global_mean(mine).numpy(), var=mpi.global_variance(mine).numpy(),
+               spp=mpi.distribute_sampling(N), fsid=mpi.first_sample_id(),
+               bcast=mpi.bcast_unknown_size(np.arange(4, dtype=np.float64) if rank == 0 else None))
+    # the packed two-collective pattern of tdvp.py: first moments, then second moments about the global mean
+    packed = torch.cat([mine.sum(dim=(0, 1)), (mine ** 2).sum(dim=(0, 1))])
+    mpi.allreduce_(packed)
+    out["packed"] = packed.numpy()
+    q.put(out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_reductions_over_gloo():
+    ctx = mp.get_context("spawn")
+    q, port = ctx.Queue(), _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda r: r["rank"])
+    [p.join(timeout=60) for p in procs]
+    full = np.random.default_rng(0).normal(size=(11, 3))
+    assert [r["size"] for r in res] == [2, 2] and [(r["first"], r["n"]) for r in res] == [(0, 6), (6, 5)]
+    for r in res:
+        assert np.allclose(r["sum"], full.sum(0)) and np.allclose(r["mean"], full.mean(0)) and np.allclose(r["var"], full.var(0))
+        assert np.allclose(r["packed"], np.concatenate([full.sum(0), (full ** 2).sum(0)]))
+        assert np.array_equal(r["bcast"], np.arange(4.0))
+    assert [r["spp"] for r in res] == [6, 5] and [r["fsid"] for r in res] == [0, 6]

@@ -1,0 +1,129 @@
+"""CPU: the __host__ __device__ math of the CUDA kernels, compiled for the host (test tooling), against the oracle."""
+import ctypes as C
+import numpy as np
+import pytest
+import torch
+
+from oracle import flow, tdvp
+from vmc_pde_b200 import _capi
+
+dp = C.POINTER(C.c_double)
+
+
+def P(a):
+    return a.ctypes.data_as(dp) if a is not None else None
+
+
+def relerr(a, b):
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-300))
+
+
+CASES = [(2, 4, 1, "no_add", "Gauss", "diffusion"),
+         (2, 4, 7, "no_add", "Gauss", "advection_paper"),
+         (6, 3, 5, "different_add", "Gauss", "advection_hamiltonian_wDiss"),
+         (6, 2, 4, "no_add", "Student_t", "diffusion_drift"),
+         (4, 2, 3, "add_s", "Gauss", "diffusion_anisotropic"),
+         (4, 2, 3, "jac_eq_1", "Student_t", "advection_hamiltonian"),
+         (5, 2, 3, "no_add", "Gauss", "diffusion"),
+         (8, 12, 4, "no_add", "Student_t", "diffusion"),   # depth > 10: blocks_10 sorts before blocks_2
+         (6, 0, 1, "no_add", "Gauss", "diffusion")]
+
+
+@pytest.mark.parametrize("d,depth,h,variant,latent,eqname", CASES)
+def test_local_terms_and_sampling_match_autograd(hostsim, d, depth, h, variant, latent, eqname):
+    rng = np.random.default_rng(d * 100 + depth)
+    n = 24
+    ups, downs, _ = flow.make_index_splits(d, depth, 1)
+    off = rng.normal(size=d) * 0.3
+    spec = flow.FlowSpec(dim=d, depth=depth, hidden=(h,), latent=latent, variant=variant, offset=off, inds_up=ups, inds_down=downs)
+    th = flow.init_params(spec, 1) + 0.05 * rng.normal(size=spec.num_params)
+    sl, _ = spec.slices()
+    for name, (a, b, shp) in sl.items():
+        if name.endswith("Dense_1/kernel"):
+            th[a:b] = 0.03 * rng.normal(size=b - a)
+    st = flow.OracleState(spec, th)
+    x = rng.normal(size=(n, d)) * 1.5
+    cfg, keep = _capi.make_flow_config(d, depth, (h,), variant, latent, ups, downs, off)
+    assert hostsim.hostsim_num_params(C.byref(cfg)) == spec.num_params
+    A = np.ascontiguousarray(tdvp.random_D_factor(d)) if eqname == "diffusion_anisotropic" else None
+    eq = _capi.make_equation(eqname, dict(tdvp.EQ_PARAMS.get(eqname, {})), 0.3, A.ctypes.data if A is not None else None)
+    Pn = spec.num_params
+    eloc, logp, lap = np.zeros(n), np.zeros(n), np.zeros(n)
+    grad, gx, O = np.zeros((n, d)), np.zeros((n, d)), np.zeros((n, Pn))
+    assert hostsim.hostsim_local_terms(C.byref(cfg), P(th), P(x), C.c_long(n), C.byref(eq), P(eloc), P(logp), P(grad), P(lap),
+                                       P(O), C.c_long(Pn), P(gx)) == 0
+    E_o, O_o, lp_o, g_o = tdvp.local_terms(st, x, eqname, 0.3)
+    tol = 1e-10
+    assert relerr(logp, lp_o.numpy()) < tol and relerr(eloc, E_o.numpy()) < tol
+    assert relerr(O, O_o.numpy()) < tol and relerr(gx, g_o.numpy()) < tol
+    if eqname != "diffusion_anisotropic":
+        assert relerr(grad, g_o.numpy()) < tol
+    H = np.zeros((n, d, d))
+    assert hostsim.hostsim_hessian(C.byref(cfg), P(th), P(x), C.c_long(n), P(H)) == 0
+    assert relerr(H, st.hessian(x).numpy()) < 1e-9
+    # sampling path: latent -> (x, logp); and log p evaluated at the produced x agrees
+    z = rng.normal(size=(n, d))
+    xs, lps, lp2 = np.zeros((n, d)), np.zeros(n), np.zeros(n)
+    assert hostsim.hostsim_sample_from_latent(C.byref(cfg), P(th), P(z), C.c_long(n), P(xs), P(lps)) == 0
+    xo, lpo = torch.func.vmap(lambda zi: flow.sample_single(zi, st.theta, spec, st.sl))(torch.as_tensor(z))
+    assert relerr(xs, xo.numpy()) < tol and relerr(lps, lpo.numpy()) < tol
+    hostsim.hostsim_logp(C.byref(cfg), P(th), P(xs), C.c_long(n), P(lp2))
+    assert relerr(lp2, lps) < 1e-10
+
+
+def test_flow_config_validation(hostsim):
+    cfg, keep = _capi.make_flow_config(4, 1, (3,), "no_add", "Gauss", [[0, 0]], [[1, 2]], np.zeros(4))
+    assert hostsim.hostsim_num_params(C.byref(cfg)) == -1  # ind_up / ind_down do not partition range(dim)
+
+
+def _dc(hostsim, d, e):
+    n = len(d)
+    lam, QT = np.zeros(n), np.zeros((n, n))
+    hostsim.hostsim_dc_eigh(n, P(d), P(e), P(lam), P(QT))
+    T = np.diag(d) + np.diag(e, 1) + np.diag(e, -1)
+    ref = np.linalg.eigvalsh(T)
+    nrm = max(np.abs(ref).max(), 1e-300)
+    return (np.abs(lam - ref).max() / nrm, np.abs(T @ QT.T - QT.T * lam).max() / nrm, np.abs(QT @ QT.T - np.eye(n)).max(),
+            bool(np.all(np.diff(lam) >= 0)))
+
+
+def test_divide_and_conquer_core_against_lapack(hostsim):
+    rng = np.random.default_rng(0)
+    mats = [(rng.normal(size=n), rng.normal(size=max(n - 1, 0))) for n in (1, 2, 3, 5, 37, 64, 257, 600)]
+    n = 300
+    mats += [(np.abs(np.arange(n) - n // 2).astype(float), np.ones(n - 1)),              # Wilkinson-like
+             (np.repeat([1.0, 2.0], n // 2), 1e-9 * rng.normal(size=n - 1)),             # two clusters
+             (np.ones(n), 1e-14 * np.ones(n - 1)),                                       # glued identity
+             (rng.normal(size=n), np.zeros(n - 1)),                                      # already diagonal
+             (10.0 ** (-np.arange(n) / 20.0), 10.0 ** (-np.arange(n - 1) / 20.0) * 0.3)]  # graded over 15 decades
+    from scipy.linalg import hessenberg
+    A = rng.normal(size=(500, 120)) @ rng.normal(size=(120, 300))
+    Hh = hessenberg(A.T @ A / 500)                                                        # rank-deficient Gram
+    mats.append((np.diag(Hh).copy(), np.diag(Hh, 1).copy()))
+    for d, e in mats:
+        ev_err, resid, orth, srt = _dc(hostsim, d, e)
+        assert ev_err < 5e-14 and resid < 5e-14 and orth < 5e-14 and srt
+
+
+def test_secular_roots_extended_precision(hostsim):
+    rng = np.random.default_rng(2)
+    k = 120
+    dl = np.sort(rng.normal(size=k))
+    w = rng.normal(size=k) * 10.0 ** (-rng.uniform(0, 7.5, size=k))
+    w /= np.linalg.norm(w)
+    w2, rho = w * w, 0.7
+    org, tau = np.zeros(k, np.int32), np.zeros(k)
+    hostsim.hostsim_secular(k, P(dl), P(w2), C.c_double(rho), org.ctypes.data_as(C.POINTER(C.c_int)), P(tau))
+    L = np.longdouble
+    for j in range(k):
+        o = org[j]
+        f = lambda t: L(1) / L(rho) + np.sum(w2.astype(L) / ((dl.astype(L) - L(dl[o])) - t))
+        if j < k - 1:
+            lo, hi = (L(0), L(dl[j + 1] - dl[j])) if o == j else (L(dl[j] - dl[j + 1]), L(0))
+        else:
+            lo, hi = L(0), L(rho * w2.sum() * 1.0000001)
+        for _ in range(200):
+            m = (lo + hi) / 2
+            lo, hi = (m, hi) if f(m) < 0 else (lo, m)
+        ref = float((lo + hi) / 2)
+        assert abs(tau[j] - ref) <= 1e-12 * abs(ref)

@@ -11,6 +11,23 @@ from . import _lib, _capi, global_defs
 
 f64 = torch.float64
 
+# number of libvmcpde kernels launched through these wrappers (bench.py reports it as gpu_launches)
+launches = 0
+
+
+def _count(n=1):
+    global launches
+    launches += n
+
+
+def eigh_launch_count(n):
+    """Kernel launches of one vmcpde_eigh call (tridiagonalisation + divide & conquer levels + back-transform)."""
+    tri = (3 + 3 * (n - 3) + 1 if n >= 3 else 0) + 1
+    depth = 0
+    while (1 << depth) < n:
+        depth += 1
+    return tri + 1 + 10 * depth + 1
+
 
 def _dev():
     return global_defs.device()
@@ -62,6 +79,7 @@ class FlowHandle:
 
 def sample(flow, theta, key, first, n, n_total, chi2=None, want_z=False):
     """vmcpde_sample: global sample indices [first, first+n) of the n_total stream of `key`."""
+    _count(1)
     L = flow.L
     x = empty(n, flow.dim)
     logp = empty(n)
@@ -72,18 +90,21 @@ def sample(flow, theta, key, first, n, n_total, chi2=None, want_z=False):
 
 
 def normal(key, first, n, total):
+    _count(1)
     out = empty(n)
     _lib.check(_lib.load().vmcpde_normal(int(key[0]), int(key[1]), int(first), int(n), int(total), _lib.ptr(out), _lib.stream()))
     return out
 
 
 def uniform(key, first, n, total):
+    _count(1)
     out = empty(n)
     _lib.check(_lib.load().vmcpde_uniform(int(key[0]), int(key[1]), int(first), int(n), int(total), _lib.ptr(out), _lib.stream()))
     return out
 
 
 def logp(flow, theta, x):
+    _count(1)
     x = x.contiguous()
     n = x.shape[0]
     out = empty(n)
@@ -92,6 +113,7 @@ def logp(flow, theta, x):
 
 
 def transform(flow, theta, x, inverse, want_latent=False):
+    _count(1)
     x = x.contiguous()
     n = x.shape[0]
     y, lj = empty(n, flow.dim), empty(n)
@@ -102,6 +124,7 @@ def transform(flow, theta, x, inverse, want_latent=False):
 
 
 def hessian(flow, theta, x):
+    _count(1)
     x = x.contiguous()
     n = x.shape[0]
     H = empty(n, flow.dim, flow.dim)
@@ -111,6 +134,7 @@ def hessian(flow, theta, x):
 
 def local_terms(flow, theta, x, eq, O=None, ldo=0, want=("eloc", "logp", "grad", "lap")):
     """Fused local terms.  eq: _capi.Equation.  O: preallocated [rows >= n, ldo] buffer or None."""
+    _count(1)
     x = x.contiguous()
     n = x.shape[0]
     out = {k: None for k in ("eloc", "logp", "grad", "lap")}
@@ -125,10 +149,12 @@ def local_terms(flow, theta, x, eq, O=None, ldo=0, want=("eloc", "logp", "grad",
 
 
 def moments1(eloc, logp_, O, n, ldo, sums):
+    _count(1)
     _lib.check(_lib.load().vmcpde_moments1(_lib.ptr(eloc), _lib.ptr(logp_), _lib.ptr(O), int(n), int(ldo), _lib.ptr(sums), _lib.stream()))
 
 
 def center_force(O, n, ldo, meanO, eloc, logp_, meanE, dE, wE, wLp, Fsum, var_sum):
+    _count(1)
     _lib.check(_lib.load().vmcpde_center_force(_lib.ptr(O), int(n), int(ldo), _lib.ptr(meanO), _lib.ptr(eloc), _lib.ptr(logp_),
                                                float(meanE), _lib.ptr(dE), _lib.ptr(wE), _lib.ptr(wLp), _lib.ptr(Fsum),
                                                _lib.ptr(var_sum), _lib.stream()))
@@ -136,15 +162,18 @@ def center_force(O, n, ldo, meanO, eloc, logp_, meanE, dE, wE, wLp, Fsum, var_su
 
 def gram(O, n, ldo, Pp, weights, mats):
     """mats[m] += sum_i weights[m][i] O[i]^T O[i] on the upper-triangular tiles; n multiple of 16."""
+    _count(1)
     _lib.check(_lib.load().vmcpde_gram(_lib.ptr(O), int(n), int(ldo), int(Pp), len(mats), _lib.ptr_array(weights),
                                        _lib.ptr_array(mats), _lib.stream()))
 
 
 def sym_finalize(S, Pp, scale):
+    _count(1)
     _lib.check(_lib.load().vmcpde_sym_finalize(_lib.ptr(S), int(Pp), float(scale), _lib.stream()))
 
 
 def diag_shift(S, out, Pp, P, shift):
+    _count(1)
     _lib.check(_lib.load().vmcpde_diag_shift(_lib.ptr(S), _lib.ptr(out), int(Pp), int(P), float(shift), _lib.stream()))
 
 
@@ -186,12 +215,14 @@ def eigh_workspace_bytes(n, ld):
 
 
 def eigh(A_destroyed, n, ld, ev, VT, ws):
+    _count(eigh_launch_count(n))
     _lib.check(_lib.load().vmcpde_eigh(_lib.ptr(A_destroyed), int(n), int(ld), _lib.ptr(ev), _lib.ptr(VT), _lib.ptr(ws),
                                        ws.numel(), _lib.stream()))
 
 
 def solve_tail(ev, VT, n, ld, F, S, S0, CEO, n_glob, svdTol, snrTol, useSNR, meanE2, VtF, rhoVar, snr, invEv, update,
                scalars, ws):
+    _count(9 if CEO is not None else 6)
     _lib.check(_lib.load().vmcpde_solve_tail(_lib.ptr(ev), _lib.ptr(VT), int(n), int(ld), _lib.ptr(F), _lib.ptr(S), _lib.ptr(S0),
                                              _lib.ptr(CEO), float(n_glob), float(svdTol), float(snrTol), int(bool(useSNR)),
                                              float(meanE2), _lib.ptr(VtF), _lib.ptr(rhoVar), _lib.ptr(snr), _lib.ptr(invEv),
@@ -199,11 +230,13 @@ def solve_tail(ev, VT, n, ld, F, S, S0, CEO, n_glob, svdTol, snrTol, useSNR, mea
 
 
 def chol_solve(S_destroyed, n, ld, F, x, info):
+    _count(3 * ((n + 63) // 64) + 1)
     _lib.check(_lib.load().vmcpde_chol_solve(_lib.ptr(S_destroyed), int(n), int(ld), _lib.ptr(F), _lib.ptr(x), _lib.ptr(info),
                                              _lib.stream()))
 
 
 def solve_scalars(S, S0, n, ld, F, update, meanE2, scalars, work2n):
+    _count(3)
     _lib.check(_lib.load().vmcpde_solve_scalars(_lib.ptr(S), _lib.ptr(S0), int(n), int(ld), _lib.ptr(F), _lib.ptr(update),
                                                 float(meanE2), _lib.ptr(scalars), _lib.ptr(work2n), _lib.stream()))
 
@@ -215,16 +248,19 @@ def obs_workspace(d):
 
 
 def obs_first(x, logp_, eloc, n, d, first, ws):
+    _count(2)
     _lib.check(_lib.load().vmcpde_obs_first(_lib.ptr(x), _lib.ptr(logp_), _lib.ptr(eloc), int(n), int(d), _lib.ptr(first),
                                             _lib.ptr(ws), _lib.stream()))
 
 
 def obs_central(x, n, d, mean, central, ws):
+    _count(2)
     _lib.check(_lib.load().vmcpde_obs_central(_lib.ptr(x), int(n), int(d), _lib.ptr(mean), _lib.ptr(central), _lib.ptr(ws),
                                               _lib.stream()))
 
 
 def ball_points(key, first, n, n_total, d, radius):
+    _count(1)
     out = empty(n, d)
     _lib.check(_lib.load().vmcpde_ball_points(int(key[0]), int(key[1]), int(first), int(n), int(n_total), int(d), float(radius),
                                               _lib.ptr(out), _lib.stream()))
@@ -232,6 +268,7 @@ def ball_points(key, first, n, n_total, d, radius):
 
 
 def sum_exp(logp_, n, out, ws):
+    _count(2)
     _lib.check(_lib.load().vmcpde_sum_exp(_lib.ptr(logp_), int(n), _lib.ptr(out), _lib.ptr(ws), _lib.stream()))
 
 

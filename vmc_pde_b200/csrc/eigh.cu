@@ -95,26 +95,79 @@ __global__ void __launch_bounds__(1024) tridiag_w_kernel(const double* __restric
   for (int i = threadIdx.x; i < m; i += blockDim.x) p[i] = t * p[i] + alpha * v[i];
 }
 
-// A22 -= v w^T + w v^T
-__global__ void __launch_bounds__(256) tridiag_rank2_kernel(double* __restrict__ A, int ld, int n, int j,
-                                                            const double* __restrict__ w) {
+// ---- fused step: the pending rank-2 update of step j is applied while the next Householder vector is formed
+// and multiplied, so the trailing matrix is read and written once per column (16 B / element instead of 24).
+
+// first row of A22(j) (global row j+1): apply the pending update, then form the next reflector from it
+__global__ void __launch_bounds__(1024) tridiag_next_house_kernel(double* __restrict__ A, int ld, int n, int j,
+                                                                 const double* __restrict__ w, double* __restrict__ d,
+                                                                 double* __restrict__ e, double* __restrict__ tau) {
+  __shared__ double sh[33];
+  const int m = n - j - 1;                       // size of A22(j)
+  const double* v = A + (size_t)j * ld + j + 1;  // v_j
+  double* row = A + (size_t)(j + 1) * ld + j + 1;
+  const double v0 = v[0], w0 = w[0];
+  double s = 0.0;
+  for (int c = threadIdx.x; c < m; c += blockDim.x) {
+    const double a = row[c] - (v0 * w[c] + w0 * v[c]);
+    row[c] = a;
+    if (c >= 2) s += a * a;
+  }
+  const double sigma = block_sum(s, sh);
+  __syncthreads();
+  // x = row[1..m): alpha = row[1], rest from c = 2
+  const double alpha = row[1];
+  double* x = row + 1;
+  const int mx = m - 1;
+  if (sigma == 0.0) {
+    if (threadIdx.x == 0) { d[j + 1] = row[0]; e[j + 1] = alpha; tau[j + 1] = 0.0; x[0] = 1.0; }
+    return;
+  }
+  const double beta = -copysign(sqrt(alpha * alpha + sigma), alpha);
+  const double scale = 1.0 / (alpha - beta);
+  for (int i = 1 + threadIdx.x; i < mx; i += blockDim.x) x[i] *= scale;
+  if (threadIdx.x == 0) { d[j + 1] = row[0]; e[j + 1] = beta; tau[j + 1] = (beta - alpha) / beta; x[0] = 1.0; }
+}
+
+// rows r >= 1, cols c >= 1 of A22(j): a' = a - v_j[r] w_j[c] - w_j[r] v_j[c]; p'[r-1] = sum_c a' * v_{j+1}[c-1]
+__global__ void __launch_bounds__(256) tridiag_update_symv_kernel(double* __restrict__ A, int ld, int n, int j,
+                                                                 const double* __restrict__ w, double* __restrict__ pn) {
   const int m = n - j - 1;
-  const double* v = A + (size_t)j * ld + j + 1;
+  const double* v = A + (size_t)j * ld + j + 1;         // v_j, indices 0..m-1
+  const double* vn = A + (size_t)(j + 1) * ld + j + 2;  // v_{j+1}, indices 0..m-2  (column c <-> vn[c-1])
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
-  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < m; r += gridDim.x * wpb) {
+  for (int r = 1 + blockIdx.x * wpb + (threadIdx.x >> 5); r < m; r += gridDim.x * wpb) {
     double* row = A + (size_t)(j + 1 + r) * ld + j + 1;
     const double vr = v[r], wr = w[r];
-    int c = lane;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int c = 1 + lane;
     for (; c + 96 < m; c += 128) {
-      const double a0 = row[c], a1 = row[c + 32], a2 = row[c + 64], a3 = row[c + 96];
-      row[c] = a0 - (vr * w[c] + wr * v[c]);
-      row[c + 32] = a1 - (vr * w[c + 32] + wr * v[c + 32]);
-      row[c + 64] = a2 - (vr * w[c + 64] + wr * v[c + 64]);
-      row[c + 96] = a3 - (vr * w[c + 96] + wr * v[c + 96]);
+      double a0 = row[c], a1 = row[c + 32], a2 = row[c + 64], a3 = row[c + 96];
+      a0 -= vr * w[c] + wr * v[c];
+      a1 -= vr * w[c + 32] + wr * v[c + 32];
+      a2 -= vr * w[c + 64] + wr * v[c + 64];
+      a3 -= vr * w[c + 96] + wr * v[c + 96];
+      row[c] = a0; row[c + 32] = a1; row[c + 64] = a2; row[c + 96] = a3;
+      s0 = fma(a0, vn[c - 1], s0); s1 = fma(a1, vn[c + 31], s1); s2 = fma(a2, vn[c + 63], s2); s3 = fma(a3, vn[c + 95], s3);
     }
-    for (; c < m; c += 32) row[c] -= vr * w[c] + wr * v[c];
+    for (; c < m; c += 32) {
+      const double a0 = row[c] - (vr * w[c] + wr * v[c]);
+      row[c] = a0;
+      s0 = fma(a0, vn[c - 1], s0);
+    }
+    const double sum = warp_sum((s0 + s1) + (s2 + s3));
+    if (lane == 0) pn[r - 1] = sum;
   }
+}
+
+// w_{j+1} from p' (tridiag_w_kernel with the next reflector); separate name for clarity of the launch sequence
+// last pending update on the final 2x2 block
+__global__ void tridiag_last_update_kernel(double* __restrict__ A, int ld, int n, int j, const double* __restrict__ w) {
+  const int m = n - j - 1;
+  const double* v = A + (size_t)j * ld + j + 1;
+  const int r = threadIdx.x / m, c = threadIdx.x % m;
+  if (r < m) A[(size_t)(j + 1 + r) * ld + j + 1 + c] -= v[r] * w[c] + w[r] * v[c];
 }
 
 __global__ void tridiag_tail_kernel(const double* __restrict__ A, int ld, int n, double* __restrict__ d,
@@ -414,7 +467,8 @@ __global__ void __launch_bounds__(256) dc_copy_deflated_kernel(DcBuf b, int dept
 // ================================================================================================
 // Stage 3: back-transformation  VT[k][:] = ZT[k][:] * H_{n-3} ... H_0   (rows independent)
 // ================================================================================================
-__global__ void __launch_bounds__(256) backtransform_kernel(const double* __restrict__ ZT, double* __restrict__ VT,
+// Generic version (any n <= 25600): rows live in shared memory.
+__global__ void __launch_bounds__(256) backtransform_smem_kernel(const double* __restrict__ ZT, double* __restrict__ VT,
                                                             const double* __restrict__ A, const double* __restrict__ tau,
                                                             int n, int ld, int rows_per_cta) {
   extern __shared__ double rows[];  // rows_per_cta * n, then 2 * 8 * rows_per_cta partials
@@ -473,6 +527,88 @@ __global__ void __launch_bounds__(256) backtransform_kernel(const double* __rest
     for (int c = threadIdx.x; c < n; c += blockDim.x) VT[(size_t)(r0 + r) * ld + c] = rows[(size_t)r * n + c];
 }
 
+
+// Fast version for n <= 8192: each thread owns columns c = tid + k*1024 (k < CPT) of ROWS eigenvector rows and keeps
+// them in registers for the whole sweep; reflectors stream through a double-buffered shared-memory stage filled with
+// cp.async by the threads that will consume them (no cross-thread hand-off).
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+template <int CPT, int ROWS>
+__global__ void __launch_bounds__(1024, 1) backtransform_reg_kernel(const double* __restrict__ ZT, double* __restrict__ VT,
+                                                                    const double* __restrict__ A, const double* __restrict__ tau,
+                                                                    int n, int ld) {
+  extern __shared__ double vstage[];  // [2][CPT * 1024]
+  __shared__ double part[2][32][ROWS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r0 = blockIdx.x * ROWS;
+  double x[ROWS][CPT];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+      const int c = tid + k * 1024;
+      x[r][k] = (r0 + r < n && c < n) ? ZT[(size_t)(r0 + r) * ld + c] : 0.0;
+    }
+  auto prefetch = [&](int j, int buf) {
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+      const int c = tid + k * 1024;
+      if (c > j && c < n) cp_async8(&vstage[buf * CPT * 1024 + c], A + (size_t)j * ld + c);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (n >= 3) prefetch(n - 3, 0);
+  int par = 0, buf = 0;
+  for (int j = n - 3; j >= 0; --j) {
+    if (j > 0) prefetch(j - 1, buf ^ 1);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    const double t = tau[j];
+    const double* vs = vstage + buf * CPT * 1024;
+    buf ^= 1;
+    if (t == 0.0) continue;
+    double v[CPT];
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) { const int c = tid + k * 1024; v[k] = (c > j && c < n) ? vs[c] : 0.0; }
+    double sdot[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < CPT; ++k) acc = fma(v[k], x[r][k], acc);
+      sdot[r] = warp_sum(acc);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) part[par][warp][r] = sdot[r];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const double tot = t * warp_sum(part[par][lane][r]);
+#pragma unroll
+      for (int k = 0; k < CPT; ++k) x[r][k] = fma(-tot, v[k], x[r][k]);
+    }
+    par ^= 1;
+  }
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+      const int c = tid + k * 1024;
+      if (r0 + r < n && c < n) VT[(size_t)(r0 + r) * ld + c] = x[r][k];
+    }
+}
+
+template <int CPT, int ROWS>
+static int launch_backtransform(const double* ZT, double* VT, const double* A, const double* tau, int n, int ld, cudaStream_t s) {
+  const size_t smem = (size_t)2 * CPT * 1024 * 8;
+  VMC_CUDA_CHECK(cudaFuncSetAttribute(backtransform_reg_kernel<CPT, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  backtransform_reg_kernel<CPT, ROWS><<<(n + ROWS - 1) / ROWS, 1024, smem, s>>>(ZT, VT, A, tau, n, ld);
+  return 0;
+}
+
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace vmc
@@ -483,7 +619,7 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_eigh_workspace_byte
   VMC_REQUIRE(bytes && n >= 1 && ld >= n, "vmcpde_eigh_workspace_bytes: bad arguments");
   size_t b = 0;
   b += 2 * align_up((size_t)n * ld * 8, 256);           // QT ping buffer, U
-  b += 16 * align_up((size_t)(n + 8) * 8, 256);          // double vectors
+  b += 17 * align_up((size_t)(n + 8) * 8, 256);          // double vectors
   b += 8 * align_up((size_t)(n + 8) * 4, 256);           // int vectors
   b += align_up((size_t)(n + 8) * sizeof(DcRot), 256);  // rotations
   *bytes = b;
@@ -500,7 +636,7 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_eigh(double* S, int
   size_t need = 0;
   vmcpde_eigh_workspace_bytes(n, ld, &need);
   VMC_REQUIRE(workspace_bytes >= need, "vmcpde_eigh: workspace too small");
-  VMC_REQUIRE((size_t)n * 8 + 1024 <= 200 * 1024, "vmcpde_eigh: n > 25472 not supported in this release");
+  VMC_REQUIRE(n <= 25 * 1024, "vmcpde_eigh: n > 25600 not supported in this release");
   cudaStream_t s = (cudaStream_t)stream;
   uint8_t* wp = (uint8_t*)workspace;
   auto take = [&](size_t bytes) { void* p = wp; wp += align_up(bytes, 256); return p; };
@@ -508,7 +644,7 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_eigh(double* S, int
   double* U = (double*)take((size_t)n * ld * 8);
   auto dvec = [&]() { return (double*)take((size_t)(n + 8) * 8); };
   auto ivec = [&]() { return (int*)take((size_t)(n + 8) * 4); };
-  double *d = dvec(), *e = dvec(), *tau = dvec(), *p = dvec();
+  double *d = dvec(), *e = dvec(), *tau = dvec(), *p = dvec(), *p2 = dvec();
   DcBuf b{};
   b.n = n; b.ld = ld; b.e = e;
   b.lam = dvec(); b.lam_new = dvec();
@@ -523,13 +659,28 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_eigh(double* S, int
   if (timing) { for (auto& e_ : evt) cudaEventCreate(&e_); cudaEventRecord(evt[0], s); }
   // ---- stage 1
   const int sms = num_sms();
-  for (int j = 0; j + 2 < n; ++j) {
-    const int m = n - j - 1;
-    const int blocks = max(1, min(sms * 4, (m + 7) / 8));
-    tridiag_house_kernel<<<1, 1024, 0, s>>>(S, ld, n, j, d, e, tau);
-    tridiag_symv_kernel<<<blocks, 256, 0, s>>>(S, ld, n, j, p);
-    tridiag_w_kernel<<<1, 1024, 0, s>>>(S, ld, n, j, tau, p);
-    tridiag_rank2_kernel<<<blocks, 256, 0, s>>>(S, ld, n, j, p);
+  if (n >= 3) {
+    double* wbuf[2] = {p, p2};
+    {  // prologue: reflector 0 and its w
+      const int m = n - 1;
+      const int blocks = max(1, min(sms * 8, (m + 7) / 8));
+      tridiag_house_kernel<<<1, 1024, 0, s>>>(S, ld, n, 0, d, e, tau);
+      tridiag_symv_kernel<<<blocks, 256, 0, s>>>(S, ld, n, 0, wbuf[0]);
+      tridiag_w_kernel<<<1, 1024, 0, s>>>(S, ld, n, 0, tau, wbuf[0]);
+    }
+    for (int j = 0; j + 2 < n; ++j) {
+      const int m = n - j - 1;
+      double* wj = wbuf[j & 1];
+      double* wn = wbuf[(j + 1) & 1];
+      if (j + 3 < n) {
+        const int blocks = max(1, min(sms * 8, (m - 1 + 7) / 8));
+        tridiag_next_house_kernel<<<1, 1024, 0, s>>>(S, ld, n, j, wj, d, e, tau);
+        tridiag_update_symv_kernel<<<blocks, 256, 0, s>>>(S, ld, n, j, wj, wn);
+        tridiag_w_kernel<<<1, 1024, 0, s>>>(S, ld, n, j + 1, tau, wn);
+      } else {
+        tridiag_last_update_kernel<<<1, 32, 0, s>>>(S, ld, n, j, wj);  // m == 2
+      }
+    }
   }
   tridiag_tail_kernel<<<1, 32, 0, s>>>(S, ld, n, d, e);
   VMC_LAUNCH_CHECK("tridiagonalisation");
@@ -542,7 +693,6 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_eigh(double* S, int
   static bool attr = false;
   if (!attr) {
     VMC_CUDA_CHECK(cudaFuncSetAttribute(dc_deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDeflateSmemMax * 20 + 64));
-    VMC_CUDA_CHECK(cudaFuncSetAttribute(backtransform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr = true;
   }
   for (int depth = D - 1; depth >= 0; --depth) {
@@ -574,13 +724,23 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_eigh(double* S, int
     VMC_CUDA_CHECK(cudaMemcpyAsync(QTb, VT, (size_t)n * ld * 8, cudaMemcpyDeviceToDevice, s));
     ZT = QTb;
   }
-  int rpc = (int)((200 * 1024 - 1024) / ((size_t)n * 8));
-  if (rpc > 4) rpc = 4;
-  if (rpc < 1) rpc = 1;
-  // keep at least ~2 CTAs per SM worth of work when n is small
-  while (rpc > 1 && (n + rpc - 1) / rpc < sms) --rpc;
-  const size_t bsm = (size_t)rpc * n * 8 + 2 * 8 * 4 * 8;
-  backtransform_kernel<<<(n + rpc - 1) / rpc, 256, bsm, s>>>(ZT, VT, S, tau, n, ld, rpc);
+  {
+    const int cpt = (n + 1023) / 1024;
+    int rc = 0;
+    if (cpt <= 1) rc = launch_backtransform<1, 8>(ZT, VT, S, tau, n, ld, s);
+    else if (cpt <= 2) rc = launch_backtransform<2, 8>(ZT, VT, S, tau, n, ld, s);
+    else if (cpt <= 4) rc = launch_backtransform<4, 4>(ZT, VT, S, tau, n, ld, s);
+    else if (cpt <= 8) rc = launch_backtransform<8, 2>(ZT, VT, S, tau, n, ld, s);
+    else {
+      int rpc = (int)((200 * 1024 - 1024) / ((size_t)n * 8));
+      if (rpc > 4) rpc = 4;
+      if (rpc < 1) rpc = 1;
+      const size_t bsm = (size_t)rpc * n * 8 + 2 * 8 * 4 * 8;
+      VMC_CUDA_CHECK(cudaFuncSetAttribute(backtransform_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      backtransform_smem_kernel<<<(n + rpc - 1) / rpc, 256, bsm, s>>>(ZT, VT, S, tau, n, ld, rpc);
+    }
+    if (rc) return rc;
+  }
   VMC_LAUNCH_CHECK("backtransform_kernel");
   if (timing) {
     cudaEventRecord(evt[3], s);

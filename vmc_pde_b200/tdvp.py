@@ -40,7 +40,6 @@ class TDVP:
         if self.solver not in ("eigh", "cholesky"):
             raise ValueError("solver must be 'eigh' or 'cholesky'")
         self._bufP = None
-        self.gpu_launches = 0
         self.S = self.S0 = self.F0 = self.SExp = self.ev = self.V = self.VtF = None
         self.rhoVar = self.snr = self.invEv = None
         self.solverResidual = self.tdvp_error = None
@@ -72,7 +71,6 @@ class TDVP:
     # ---- pieces of get_tdvp_equation (tdvp.py:36-52) on one chunk ------------------------------------
     def _pass1_chunk(self, E, lp, O, n, ldo, first):
         _kernels.moments1(E, lp, O, n, ldo, first)
-        self.gpu_launches += 1
 
     def _pass2_chunk(self, E, lp, O, n, n_pad, ldo, Pp, meanO, meanE, scratch):
         S0, SExp, CEO, Fsum, var_sum = self._mats(Pp)
@@ -86,7 +84,6 @@ class TDVP:
         if self.computeSNR and self.solver == "eigh":
             mats.append(CEO); weights.append(wE)
         _kernels.gram(O, n_pad, ldo, Pp, weights, mats)
-        self.gpu_launches += 2
 
     def _finish(self, P, Pp, N, first):
         """All-reduce of the second moments, normalisation, regularised solve (tdvp.py:50-51,57-94)."""
@@ -130,7 +127,6 @@ class TDVP:
             if int(self._info.item()) != 0:
                 raise RuntimeError(f"Cholesky failed: non-positive pivot at index {int(self._info.item()) - 1}")
             self.ev = self.V = self.VtF = self.invEv = self.rhoVar = self.snr = None
-        self.gpu_launches += 8
         self.solverResidual, self.tdvp_error = self._scal[0].clone(), self._scal[1].clone()
         return update[:P].clone()
 
@@ -265,7 +261,6 @@ class TDVP:
             out = _kernels.local_terms(h, psi._flat, x_all[c0:c0 + cn], eq, O=O, ldo=Pp, want=("eloc", "logp"))
             E_all[c0:c0 + cn] = out["eloc"]; lp_all[c0:c0 + cn] = out["logp"]
             toc("compute Eloc", t0)
-            self.gpu_launches += 2 if sample else 1
 
         # pass 1: samples, local terms, first moments (tdvp.py:117-122,37-41)
         for c0, cn in chunks:
@@ -345,5 +340,4 @@ class TDVP:
             lim = lim_normal * math.sqrt(T)
             sphere_volume = math.pi ** (d / 2) / scipy.special.gamma(d / 2 + 1) * lim ** d
             info[f"integral_{lim_normal}sigma"] = sums[j] / nSamplesObs * sphere_volume
-        self.gpu_launches += 12
         return info
