@@ -33,8 +33,12 @@ for i, r in enumerate(srows):
         for q in sorted(body, key=lambda q: -int(q[idx["# Samples"]]))[:15]:
             st = {h.replace("stall_", ""): int(q[idx[h]]) for h in h2 if h.startswith("stall_") and "Not Issued" not in h and int(q[idx[h]]) > 0.1 * int(q[idx["# Samples"]])}
             lines.append(f"  {100.0 * int(q[idx['# Samples']]) / tot:5.1f}%  {q[idx['Source']].strip()[:58]:58s} {st}")
-        exc = sum(int(q[idx["L1 Wavefronts Shared Excessive"]]) for q in body); wf = sum(int(q[idx["L1 Wavefronts Shared"]]) for q in body)
-        lines.append(f"shared wavefronts {wf}, excessive {exc}")
+        if "L1 Wavefronts Shared Excessive" in idx:
+            exc = sum(int(q[idx["L1 Wavefronts Shared Excessive"]] or 0) for q in body); wf = sum(int(q[idx["L1 Wavefronts Shared"]] or 0) for q in body)
+            lines.append(f"shared wavefronts {wf}, excessive {exc}")
+        if "L2 Theoretical Sectors Global Excessive" in idx:
+            exg = sum(int(q[idx["L2 Theoretical Sectors Global Excessive"]] or 0) for q in body); sg = sum(int(q[idx["L2 Theoretical Sectors Global"]] or 0) for q in body)
+            lines.append(f"L2 theoretical sectors global {sg}, excessive {exg}")
         mn = {}
         for q in body:
             op = q[idx["Source"]].strip().split()
