@@ -151,12 +151,17 @@ int vmcpde_dmma_peak(double* tflops_out);
 
 /* ---- (4) regularised solve -------------------------------------------------------------------- */
 /* Symmetric eigendecomposition on the device, replacing np.linalg.eigh at tdvp.py:61-64.
- * S (n x n, leading dimension ld, full symmetric) is destroyed; ev[n] ascending; VT row k = eigenvector k
- * (n x ld; the caller zero-fills the padding).  Householder tridiagonalisation + divide & conquer +
- * back-transformation, no host synchronisation.  n <= 25472 in this release. */
+ * S (full symmetric, leading dimension ld) is destroyed; ev[n] ascending; VT row k = eigenvector k.
+ * S and VT are ld x ld buffers with finite (zero) padding outside n x n when ld is a multiple of 128 >= n -- the
+ * layout every caller in this package uses; then the blocked path runs for n >= 384: panel tridiagonalisation in a
+ * persistent cooperative kernel (trailing matrix read once per column, rank-2nb update on FP64 tensor cores),
+ * divide & conquer, compact-WY back-transformation as tensor-core products.  Otherwise (small n or unpadded ld,
+ * S and VT n x ld) the unblocked kernels run.  No host synchronisation.  n <= 25472 in this release. */
 int vmcpde_eigh_workspace_bytes(int32_t n, int32_t ld, size_t* bytes);
 int vmcpde_eigh(double* S, int32_t n, int32_t ld, double* ev, double* VT, void* workspace,
                 size_t workspace_bytes, vmcpde_stream stream);
+/* number of kernel launches one vmcpde_eigh(n, ld) call issues */
+int vmcpde_eigh_launch_count(int32_t n, int32_t ld, int32_t* count);
 /* Everything after eigh in TDVP.transform_to_eigenbasis / TDVP.solve (tdvp.py:66-94): VtF = V^T F;
  * rhoVar = diag(V^T CEO V) - VtF^2 and snr = sqrt|N VtF^2 / rhoVar| when CEO (the dE^2-weighted Gram, ld x ld,
  * zero padded) is given; invEv = (|ev/ev_max| > 1e-14) ? 1/ev : 0; regulariser 1/(1+(svdTol/|ev/ev_max|)^6)

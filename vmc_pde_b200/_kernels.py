@@ -20,13 +20,11 @@ def _count(n=1):
     launches += n
 
 
-def eigh_launch_count(n):
+def eigh_launch_count(n, ld):
     """Kernel launches of one vmcpde_eigh call (tridiagonalisation + divide & conquer levels + back-transform)."""
-    tri = (3 + 3 * (n - 3) + 1 if n >= 3 else 0) + 1
-    depth = 0
-    while (1 << depth) < n:
-        depth += 1
-    return tri + 1 + 10 * depth + 1
+    c = C.c_int32(0)
+    _lib.check(_lib.load().vmcpde_eigh_launch_count(int(n), int(ld), C.byref(c)))
+    return c.value
 
 
 def _dev():
@@ -215,7 +213,7 @@ def eigh_workspace_bytes(n, ld):
 
 
 def eigh(A_destroyed, n, ld, ev, VT, ws):
-    _count(eigh_launch_count(n))
+    _count(eigh_launch_count(n, ld))
     _lib.check(_lib.load().vmcpde_eigh(_lib.ptr(A_destroyed), int(n), int(ld), _lib.ptr(ev), _lib.ptr(VT), _lib.ptr(ws),
                                        ws.numel(), _lib.stream()))
 

@@ -39,6 +39,7 @@ SIGNATURES = {
     "vmcpde_gemm_tn": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i64, _dbl, _dbl, _vp]),
     "vmcpde_eigh_workspace_bytes": (C.c_int, [_i32, _i32, C.POINTER(C.c_size_t)]),
     "vmcpde_eigh": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "vmcpde_eigh_launch_count": (C.c_int, [_i32, _i32, C.POINTER(_i32)]),
     "vmcpde_solve_tail_workspace_bytes": (C.c_int, [_i32, _i32, C.POINTER(C.c_size_t)]),
     "vmcpde_solve_tail": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _dbl, _dbl, _dbl, _i32, _dbl,
                                     _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),

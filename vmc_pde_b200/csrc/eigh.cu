@@ -611,6 +611,17 @@ static int launch_backtransform(const double* ZT, double* VT, const double* A, c
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// eigh_blocked.cu
+bool blocked_eigh_supported(int n, int ld);
+size_t blocked_tridiag_scratch_bytes(int n, int ld);
+size_t blocked_backtransform_scratch_bytes(int n, int ld);
+int blocked_tridiag_launches(int n);
+int blocked_backtransform_launches(int n);
+int tridiag_blocked(double* A, int n, int ld, double* d, double* e, double* tau, void* scratch, size_t scratch_bytes,
+                    cudaStream_t s);
+int backtransform_blocked(double* A, const double* tau, int n, int ld, const double* ZT, double* Zn, double* AT,
+                          void* scratch, size_t scratch_bytes, double* VT, cudaStream_t s);
+
 }  // namespace vmc
 
 using namespace vmc;
@@ -618,11 +629,25 @@ using namespace vmc;
 extern "C" __attribute__((visibility("default"))) int vmcpde_eigh_workspace_bytes(int32_t n, int32_t ld, size_t* bytes) {
   VMC_REQUIRE(bytes && n >= 1 && ld >= n, "vmcpde_eigh_workspace_bytes: bad arguments");
   size_t b = 0;
-  b += 2 * align_up((size_t)n * ld * 8, 256);           // QT ping buffer, U
+  const bool blocked = blocked_eigh_supported(n, ld);
+  const size_t rows = blocked ? (size_t)(n + 127) / 128 * 128 : (size_t)n;
+  b += 2 * align_up(rows * ld * 8, 256);                // QT ping buffer, U
+  if (blocked) b += align_up(blocked_tridiag_scratch_bytes(n, ld), 256) + align_up(blocked_backtransform_scratch_bytes(n, ld), 256);
   b += 17 * align_up((size_t)(n + 8) * 8, 256);          // double vectors
   b += 8 * align_up((size_t)(n + 8) * 4, 256);           // int vectors
   b += align_up((size_t)(n + 8) * sizeof(DcRot), 256);  // rotations
   *bytes = b;
+  return 0;
+}
+
+// Kernel launches issued by one vmcpde_eigh call (the bench reports it in gpu_launches).
+extern "C" __attribute__((visibility("default"))) int vmcpde_eigh_launch_count(int32_t n, int32_t ld, int32_t* count) {
+  VMC_REQUIRE(count && n >= 1 && ld >= n, "vmcpde_eigh_launch_count: bad arguments");
+  const int depth = dc_tree_depth(n);
+  int c = 1 + 10 * depth;  // dc_init + per-level kernels
+  if (blocked_eigh_supported(n, ld)) c += blocked_tridiag_launches(n) + blocked_backtransform_launches(n);
+  else c += (n >= 3 ? 3 + 3 * (n - 3) + 1 : 0) + 1 + 1;
+  *count = c;
   return 0;
 }
 
@@ -640,8 +665,14 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_eigh(double* S, int
   cudaStream_t s = (cudaStream_t)stream;
   uint8_t* wp = (uint8_t*)workspace;
   auto take = [&](size_t bytes) { void* p = wp; wp += align_up(bytes, 256); return p; };
-  double* QTb = (double*)take((size_t)n * ld * 8);
-  double* U = (double*)take((size_t)n * ld * 8);
+  const bool blocked = blocked_eigh_supported(n, ld);
+  const size_t rows = blocked ? (size_t)(n + 127) / 128 * 128 : (size_t)n;
+  double* QTb = (double*)take(rows * ld * 8);
+  double* U = (double*)take(rows * ld * 8);
+  const size_t tri_bytes = blocked ? blocked_tridiag_scratch_bytes(n, ld) : 0;
+  const size_t bt_bytes = blocked ? blocked_backtransform_scratch_bytes(n, ld) : 0;
+  void* tri_scratch = blocked ? take(tri_bytes) : nullptr;
+  void* bt_scratch = blocked ? take(bt_bytes) : nullptr;
   auto dvec = [&]() { return (double*)take((size_t)(n + 8) * 8); };
   auto ivec = [&]() { return (int*)take((size_t)(n + 8) * 4); };
   double *d = dvec(), *e = dvec(), *tau = dvec(), *p = dvec(), *p2 = dvec();
@@ -659,7 +690,9 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_eigh(double* S, int
   if (timing) { for (auto& e_ : evt) cudaEventCreate(&e_); cudaEventRecord(evt[0], s); }
   // ---- stage 1
   const int sms = num_sms();
-  if (n >= 3) {
+  if (blocked) {
+    if (int rc = tridiag_blocked(S, n, ld, d, e, tau, tri_scratch, tri_bytes, s)) return rc;
+  } else if (n >= 3) {
     double* wbuf[2] = {p, p2};
     {  // prologue: reflector 0 and its w
       const int m = n - 1;
@@ -682,12 +715,13 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_eigh(double* S, int
       }
     }
   }
-  tridiag_tail_kernel<<<1, 32, 0, s>>>(S, ld, n, d, e);
+  if (!blocked) tridiag_tail_kernel<<<1, 32, 0, s>>>(S, ld, n, d, e);
   VMC_LAUNCH_CHECK("tridiagonalisation");
 
   if (timing) cudaEventRecord(evt[1], s);
   // ---- stage 2 (the ping buffer must be zero outside the diagonal blocks written level by level)
-  VMC_CUDA_CHECK(cudaMemsetAsync(QTb, 0, (size_t)n * ld * 8, s));
+  VMC_CUDA_CHECK(cudaMemsetAsync(QTb, 0, rows * ld * 8, s));
+  if (rows > (size_t)n) VMC_CUDA_CHECK(cudaMemsetAsync(VT + (size_t)n * ld, 0, (rows - n) * ld * 8, s));
   dc_init_kernel<<<sms * 4, 256, 0, s>>>(b, d);
   const int D = dc_tree_depth(n);
   static bool attr = false;
@@ -720,11 +754,14 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_eigh(double* S, int
   if (timing) cudaEventRecord(evt[2], s);
   // ---- stage 3 (out of place: ZT = b.QT -> VT; if they alias, stage through the other buffer)
   const double* ZT = b.QT;
-  if (ZT == VT) {
+  if (blocked) {
+    // Zn = ZT^T lives in U, the reflector transpose in the free ping buffer; VT may alias either source
+    if (int rc = backtransform_blocked(S, tau, n, ld, ZT, U, b.QT_new, bt_scratch, bt_bytes, VT, s)) return rc;
+  } else if (ZT == VT) {
     VMC_CUDA_CHECK(cudaMemcpyAsync(QTb, VT, (size_t)n * ld * 8, cudaMemcpyDeviceToDevice, s));
     ZT = QTb;
   }
-  {
+  if (!blocked) {
     const int cpt = (n + 1023) / 1024;
     int rc = 0;
     if (cpt <= 1) rc = launch_backtransform<1, 8>(ZT, VT, S, tau, n, ld, s);
