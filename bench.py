@@ -148,13 +148,18 @@ def run_ours(args):
         host_theta.copy_(host_out[:P])
         return float(host_out[P])
 
-    peak = _kernels.dmma_peak_tflops() if rank == 0 else 0.0   # FP64 tensor peak, measured live (no entry in MEASURED_PEAKS.json)
-
     for _ in range(args.warmup):
         step_device()
     # ---- device-resident timing ----
-    gram_events = []
-    orig_gram = _kernels.gram
+    gram_events, eigh_events = [], []
+    orig_gram, orig_eigh = _kernels.gram, _kernels.eigh
+
+    def timed_eigh(*a):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig_eigh(*a)
+        e1.record()
+        eigh_events.append((e0, e1))
 
     def timed_gram(O, n, ldo, Pp, weights, mats):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -163,7 +168,7 @@ def run_ours(args):
         e1.record()
         gram_events.append((e0, e1, n, len(mats)))
 
-    _kernels.gram = timed_gram
+    _kernels.gram, _kernels.eigh = timed_gram, timed_eigh
     import vmc_pde_b200.tdvp as _t
     clocks = ClockSampler(local)
     barrier()
@@ -178,7 +183,8 @@ def run_ours(args):
     barrier()
     launches = _kernels.launches - launches0
     ms = ev0.elapsed_time(ev1)
-    _kernels.gram = orig_gram
+    _kernels.gram, _kernels.eigh = orig_gram, orig_eigh
+    eigh_ms = [a.elapsed_time(b) for a, b in eigh_events]
     gram_ms = [a.elapsed_time(b) for a, b, _, _ in gram_events]
     gram_flops = [m * n * P * (P + 1.0) for _, _, n, m in gram_events]   # SYRK convention, true P
     # ---- end-to-end timing through host buffers ----
@@ -199,6 +205,8 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
+    # FP64 tensor peak, measured live on the warm GPU right after the timed steps (MEASURED_PEAKS.json has no FP64 entry)
+    peak = _kernels.dmma_peak_tflops()
     value = args.steps / (ms * 1e-3)
     traffic = None
     prof = os.path.join(ROOT, "profiles", "gram_traffic.json")
@@ -221,6 +229,8 @@ def run_ours(args):
                      "peak_source": "measured live: register-resident DMMA.8x8x4 loop (vmcpde_dmma_peak); MEASURED_PEAKS.json has no FP64 entry",
                      "flops_convention": "n_mats * n * P * (P+1) per launch (SYRK, SURVEY 8d); launches per step: 2",
                      "share_of_step": sum(gram_ms) / ms if gram_ms else None},
+        "stages_ms_per_rhs": {"gram": sum(gram_ms) / max(len(eigh_ms), 1), "eigh": sum(eigh_ms) / max(len(eigh_ms), 1),
+                              "everything_else": (ms - sum(gram_ms) - sum(eigh_ms)) / max(len(eigh_ms), 1)},
         "last_entropy": ent,
     }
     line["cpu_baseline"] = cpu_baseline(bounded_seconds=True)

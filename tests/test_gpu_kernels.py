@@ -197,7 +197,7 @@ def _eigh(L, S_np):
 def test_eigh_against_lapack(L):
     rng = np.random.default_rng(0)
     mats = []
-    for n in (1, 2, 3, 37, 130, 300, 1000):
+    for n in (1, 2, 3, 37, 130, 300, 385, 777, 1000):   # n >= 384 takes the blocked (cooperative panel) path
         A = rng.normal(size=(n, n)); mats.append((A + A.T) / 2)
     A = rng.normal(size=(3000, 200)) @ rng.normal(size=(200, 600)); mats.append(A.T @ A / 3000)        # rank deficient
     cs = 10.0 ** (-6.0 * np.arange(1100) / 1100); A = rng.normal(size=(3000, 1100)) * cs; mats.append(A.T @ A / 3000)  # graded

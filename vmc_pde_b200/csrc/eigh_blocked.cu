@@ -100,7 +100,8 @@ __global__ void __launch_bounds__(kPT, 1) tridiag_panel_kernel(const __grid_cons
   double* rowV = PWs + nb;          // [nb]
   double* rowW = rowV + nb;         // [nb]
   double* ypart = rowW + nb;        // [S / 4][16][4]
-  double* red = ypart + S * 16;     // [64]
+  double* anext = ypart + S * 16;   // [S]
+  double* red = anext + S;          // [64]
 
   auto row_of_slot = [&](int s) { return (b + (s >> 2) * G) * kRC + (s & 3); };
   const int nq = (n + kRC - 1) / kRC;                   // ownership chunks
@@ -135,11 +136,18 @@ __global__ void __launch_bounds__(kPT, 1) tridiag_panel_kernel(const __grid_cons
       rowV[tid] = __ldcg(a.vrows + (size_t)tid * ldo + i + 1);
       rowW[tid] = __ldcg(a.wrows + (size_t)tid * ldo + i + 1);
     }
+    // next pivot row of the (panel-start) trailing matrix on the rows of this CTA: issued now, used in phase B
+    if (tid < S) {
+      const int r = row_of_slot(tid);
+      anext[tid] = (i + 1 < a.nbp && r > j && r < n) ? __ldg(a.A + (size_t)(j + 1) * ld + r) : 0.0;
+    }
     if (have) {
       // ---------------- phase A: reflector, y = A22 v on the rows of this CTA, partial dots ----------------
+      // one round trip for everything the reflector needs: norm partials and the raw pivot row
       const double sg = tid < G ? __ldcg(a.psig + tid) : 0.0;
+      for (int c = tid; c < n; c += kPT) vs[c] = c > j ? __ldcg(a.acol + c) : 0.0;
       const double sigma = bsum_(sg, red);
-      const double alpha = __ldcg(a.acol + j + 1);
+      const double alpha = vs[j + 1];
       double beta = alpha, scale = 0.0;
       if (sigma != 0.0) {
         beta = -copysign(sqrt(alpha * alpha + sigma), alpha);
@@ -147,12 +155,8 @@ __global__ void __launch_bounds__(kPT, 1) tridiag_panel_kernel(const __grid_cons
         scale = 1.0 / (alpha - beta);
       }
       if (b == 0 && tid == 0) { a.d[j] = __ldcg(a.acol + j); a.e[j] = beta; a.tau[j] = tau_j; }
-      for (int c = tid; c < n; c += kPT) {
-        double val = 0.0;
-        if (c == j + 1) val = 1.0;
-        else if (c > j + 1) val = __ldcg(a.acol + c) * scale;
-        vs[c] = val;
-      }
+      __syncthreads();  // every thread has read alpha
+      for (int c = j + 1 + tid; c < n; c += kPT) vs[c] = c == j + 1 ? 1.0 : vs[c] * scale;
       __syncthreads();
       for (int c = wlo + tid; c < whi; c += kPT) {
         const double val = vs[c];
@@ -184,7 +188,9 @@ __global__ void __launch_bounds__(kPT, 1) tridiag_panel_kernel(const __grid_cons
         segl = ((len + nseg - 1) / nseg + 63) & ~63;
       }
       const int items = kact > 0 ? kact * nseg : 0;
-      for (int item = warp; item < items; item += kPW) {
+      // odd columns walk the items backwards: what the previous column read last is still in L2
+      for (int it = warp; it < items; it += kPW) {
+        const int item = (j & 1) ? items - 1 - it : it;
         const int ch = item % kact, sgi = item / kact;
         const int r0 = (b + (lq0 + ch) * G) * kRC;
         const double* p0 = a.A + (size_t)min(r0, n - 1) * ld;
@@ -252,15 +258,33 @@ __global__ void __launch_bounds__(kPT, 1) tridiag_panel_kernel(const __grid_cons
       grid_sync(a.bar, target);
       // ---------------- phase B: reduce the partials ----------------
       const int nred = 2 * i + 1;
-      for (int t = warp; t < nred; t += kPW) {
-        const int kk = t < i ? t : (t < 2 * i ? nb + (t - i) : 2 * nb);
-        double s = 0.0;
-        for (int q = lane; q < G; q += 32) s += __ldcg(a.part + (size_t)kk * G + q);
-        s = wsum_(s);
-        if (lane == 0) {
-          if (t < i) PV[t] = s;
-          else if (t < 2 * i) PWs[t - i] = s;
-          else red[40] = s;
+      {  // all loads of a warp are issued before the first reduction (one L2 round trip instead of nred / 16)
+        constexpr int kU = 9, kQ = 5;  // 2 * 64 + 1 values over 16 warps; up to 160 CTAs
+        double acc[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const int t = warp + u * kPW;
+          const int kk = t < i ? t : (t < 2 * i ? nb + (t - i) : 2 * nb);
+          double sacc = 0.0;
+          if (t < nred) {
+#pragma unroll
+            for (int q = 0; q < kQ; ++q) {
+              const int bb = lane + 32 * q;
+              if (bb < G) sacc += __ldcg(a.part + (size_t)kk * G + bb);
+            }
+            for (int bb = lane + 32 * kQ; bb < G; bb += 32) sacc += __ldcg(a.part + (size_t)kk * G + bb);
+          }
+          acc[u] = sacc;
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const int t = warp + u * kPW;
+          const double sred = wsum_(acc[u]);
+          if (lane == 0 && t < nred) {
+            if (t < i) PV[t] = sred;
+            else if (t < 2 * i) PWs[t - i] = sred;
+            else red[40] = sred;
+          }
         }
       }
       if (tid == kPT - 1) red[41] = __ldcg(a.part + (size_t)(2 * nb + 1) * G);
@@ -319,7 +343,7 @@ __global__ void __launch_bounds__(kPT, 1) tridiag_panel_kernel(const __grid_cons
           if (r >= a.j0 && r <= a.j0 + nb) a.wrows[(size_t)i * ldo + r - a.j0] = w;
         }
         if (i + 1 < a.nbp && r > j && r < n) {  // pivot row j + 1 with all panel reflectors applied
-          const double an = a.A[(size_t)(j + 1) * ld + r] - acca - (w + w1 * vv);
+          const double an = anext[s] - acca - (w + w1 * vv);
           a.acol[r] = an;
           if (r >= j + 3) sg2 += an * an;
         }
@@ -467,7 +491,7 @@ static bool plan_panel(int n, BlockedPlan* p) {
   const int S = ((nq + G - 1) / G) * kRC;
   const int nv = (n + 2) & ~1;
   for (int nb = 64; nb >= 16; nb >>= 1) {
-    const size_t doubles = (size_t)nv + 2 * (size_t)S * (nb + 1) + 2 * S + 4 * nb + (size_t)S * 16 + 64;
+    const size_t doubles = (size_t)nv + 2 * (size_t)S * (nb + 1) + 3 * S + 4 * nb + (size_t)S * 16 + 64;
     if (doubles * 8 <= (size_t)max_smem) {
       p->nb = nb; p->S = S; p->grid = G; p->smem = doubles * 8;
       return true;

@@ -356,12 +356,12 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_dmma_peak(double* t
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  const int iters = 4000, blocks = num_sms() * 4;
-  // bring the clocks up first (a cold GPU under-reports by ~20%): ~0.3 s of the same loop, untimed
-  for (int w = 0; w < 12; ++w) dmma_peak_kernel<<<blocks, 256>>>(d, iters);
+  const int iters = 8000, blocks = num_sms() * 4;
+  // bring the clocks up first (a cold GPU under-reports by ~20%): ~0.5 s of the same loop, untimed
+  for (int w = 0; w < 60; ++w) dmma_peak_kernel<<<blocks, 256>>>(d, iters);
   cudaDeviceSynchronize();
   double best = 0.0;
-  for (int rep = 0; rep < 5; ++rep) {
+  for (int rep = 0; rep < 10; ++rep) {
     cudaEventRecord(e0);
     dmma_peak_kernel<<<blocks, 256>>>(d, iters);
     cudaEventRecord(e1);
