@@ -233,7 +233,8 @@ def run_ours(args):
                               "everything_else": (ms - sum(gram_ms) - sum(eigh_ms)) / max(len(eigh_ms), 1)},
         "last_entropy": ent,
     }
-    line["cpu_baseline"] = cpu_baseline(bounded_seconds=True)
+    # CPU arm: rank 0 at N=1 only (under torchrun the host threads are pinned to 1 per rank; see --impl reference)
+    line["cpu_baseline"] = cpu_baseline(bounded_seconds=True) if world == 1 else None
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -296,6 +297,8 @@ def run_reference(args):
     if rank != 0:
         return
     import torch
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm uses all the host threads it can
+    torch.set_num_threads(max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)))
     cpu_step_estimate(n_s=256)
     for _ in range(args.warmup):
         cpu_step_estimate(n_s=256)

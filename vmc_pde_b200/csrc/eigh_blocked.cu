@@ -49,15 +49,15 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// all CTAs of the (cooperative) grid; `target` counts the arrivals expected so far
+// all CTAs of the (cooperative) grid; `target` counts the arrivals expected so far.  The arrival is a release
+// reduction (no return value to wait for: polling starts at once), the poll an acquire load; bar.sync on both
+// sides extends the ordering to the whole CTA.
 __device__ __forceinline__ void grid_sync(unsigned* bar, unsigned& target) {
   __syncthreads();
   if (threadIdx.x == 0) {
     target += gridDim.x;
-    __threadfence();
-    atomicAdd(bar, 1u);
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
     while (ld_acquire_u32(bar) < target) {}
-    __threadfence();
   }
   __syncthreads();
 }
@@ -81,6 +81,8 @@ struct PanelArgs {
   double* wrows;           // [nb][nb + 1]: w_k(j0 + ii)
   double* X;               // [2 nb][ld]: rows k: v_k, rows nb + k: w_k, zero for index < j1
   double* Y;               // [2 nb][ld]: rows k: w_k, rows nb + k: v_k, zero for index < j1
+  double* Z;               // [grid][ld] column-part partial products of the symmetric mat-vec (NULL: full rows only)
+  int sym_min_m;           // columns with a trailing size >= this read only the lower triangle
   unsigned* bar;
 };
 
@@ -102,6 +104,7 @@ __global__ void __launch_bounds__(kPT, 1) tridiag_panel_kernel(const __grid_cons
   double* ypart = rowW + nb;        // [S / 4][16][4]
   double* anext = ypart + S * 16;   // [S]
   double* red = anext + S;          // [64]
+  double* zs = red + 64;            // [nv] (symmetric mode only)
 
   auto row_of_slot = [&](int s) { return (b + (s >> 2) * G) * kRC + (s & 3); };
   const int nq = (n + kRC - 1) / kRC;                   // ownership chunks
@@ -157,6 +160,8 @@ __global__ void __launch_bounds__(kPT, 1) tridiag_panel_kernel(const __grid_cons
       if (b == 0 && tid == 0) { a.d[j] = __ldcg(a.acol + j); a.e[j] = beta; a.tau[j] = tau_j; }
       __syncthreads();  // every thread has read alpha
       for (int c = j + 1 + tid; c < n; c += kPT) vs[c] = c == j + 1 ? 1.0 : vs[c] * scale;
+      const bool sym = a.Z != nullptr && m >= a.sym_min_m;
+      if (sym) for (int c = (j & ~1) + tid; c < nv; c += kPT) zs[c] = 0.0;
       __syncthreads();
       for (int c = wlo + tid; c < whi; c += kPT) {
         const double val = vs[c];
@@ -182,6 +187,76 @@ __global__ void __launch_bounds__(kPT, 1) tridiag_panel_kernel(const __grid_cons
       const int cs0 = (j + 1) & ~1, ce0 = n & ~1;
       const int len = ce0 - cs0;
       int nseg = 1, segl = 64;
+      if (sym) {
+        // Lower triangle only: element (r, c), c < r, serves y(r) += A v(c) (row part, reduced inside the CTA) and
+        // y(c) += A v(r) (column part, accumulated per CTA in zs and summed across CTAs after the barrier).
+        // Chunk-outer / segment-inner: a warp owns the 64-column segments g = warp (mod 16), so zs needs no atomics.
+        nseg = kPW;
+        const int nsegs = (len + 63) >> 6;
+        for (int cc = 0; cc < kact; ++cc) {
+          const int ch = (j & 1) ? kact - 1 - cc : cc;   // odd columns walk backwards (L2 reuse)
+          const int r0 = (b + (lq0 + ch) * G) * kRC;
+          const int clast = min(r0 + 3, ce0 - 1);
+          const int gmax = clast >= cs0 ? min(nsegs, ((clast - cs0) >> 6) + 1) : 0;
+          const double* p0 = a.A + (size_t)min(r0, n - 1) * ld;
+          const double* p1 = a.A + (size_t)min(r0 + 1, n - 1) * ld;
+          const double* p2 = a.A + (size_t)min(r0 + 2, n - 1) * ld;
+          const double* p3 = a.A + (size_t)min(r0 + 3, n - 1) * ld;
+          const double vr0 = r0 < n ? vs[r0] : 0.0, vr1 = r0 + 1 < n ? vs[r0 + 1] : 0.0;
+          const double vr2 = r0 + 2 < n ? vs[r0 + 2] : 0.0, vr3 = r0 + 3 < n ? vs[r0 + 3] : 0.0;
+          double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+          auto masked = [&](int c, double2 av, double vr, int r, double2 va, double& sacc, double2& z) {
+            if (c < r) { sacc = fma(av.x, va.x, sacc); z.x = fma(av.x, vr, z.x); }
+            else if (c == r) sacc = fma(av.x, va.x, sacc);
+            if (c + 1 < r) { sacc = fma(av.y, va.y, sacc); z.y = fma(av.y, vr, z.y); }
+            else if (c + 1 == r) sacc = fma(av.y, va.y, sacc);
+          };
+          auto process = [&](int c, double2 a0, double2 a1, double2 a2, double2 a3) {
+            const double2 va = *(const double2*)(vs + c);
+            double2 z = *(double2*)(zs + c);
+            if (c + 1 < r0) {  // strictly below the diagonal for all four rows
+              s0 = fma(a0.x, va.x, s0); s0 = fma(a0.y, va.y, s0);
+              s1 = fma(a1.x, va.x, s1); s1 = fma(a1.y, va.y, s1);
+              s2 = fma(a2.x, va.x, s2); s2 = fma(a2.y, va.y, s2);
+              s3 = fma(a3.x, va.x, s3); s3 = fma(a3.y, va.y, s3);
+              z.x = fma(a0.x, vr0, z.x); z.x = fma(a1.x, vr1, z.x); z.x = fma(a2.x, vr2, z.x); z.x = fma(a3.x, vr3, z.x);
+              z.y = fma(a0.y, vr0, z.y); z.y = fma(a1.y, vr1, z.y); z.y = fma(a2.y, vr2, z.y); z.y = fma(a3.y, vr3, z.y);
+            } else {
+              masked(c, a0, vr0, r0, va, s0, z); masked(c, a1, vr1, r0 + 1, va, s1, z);
+              masked(c, a2, vr2, r0 + 2, va, s2, z); masked(c, a3, vr3, r0 + 3, va, s3, z);
+            }
+            *(double2*)(zs + c) = z;
+          };
+          int g = warp;
+#pragma unroll 1
+          for (; g + kPW < gmax; g += 2 * kPW) {  // two segments per trip: 8 x 16 B in flight per lane
+            const int c = cs0 + (g << 6) + 2 * lane, c2 = c + (kPW << 6);
+            const bool in2 = c2 < ce0;   // c < ce0 always holds here: a later segment exists
+            const double2 a0 = __ldg((const double2*)(p0 + c)), a1 = __ldg((const double2*)(p1 + c));
+            const double2 a2 = __ldg((const double2*)(p2 + c)), a3 = __ldg((const double2*)(p3 + c));
+            double2 b0 = make_double2(0.0, 0.0), b1 = b0, b2 = b0, b3 = b0;
+            if (in2) {
+              b0 = __ldg((const double2*)(p0 + c2)); b1 = __ldg((const double2*)(p1 + c2));
+              b2 = __ldg((const double2*)(p2 + c2)); b3 = __ldg((const double2*)(p3 + c2));
+            }
+            process(c, a0, a1, a2, a3);
+            if (in2) process(c2, b0, b1, b2, b3);
+          }
+          if (g < gmax) {
+            const int c = cs0 + (g << 6) + 2 * lane;
+            if (c < ce0) {
+              const double2 a0 = __ldg((const double2*)(p0 + c)), a1 = __ldg((const double2*)(p1 + c));
+              const double2 a2 = __ldg((const double2*)(p2 + c)), a3 = __ldg((const double2*)(p3 + c));
+              process(c, a0, a1, a2, a3);
+            }
+          }
+          s0 = wsum_(s0); s1 = wsum_(s1); s2 = wsum_(s2); s3 = wsum_(s3);
+          if (lane == 0) {
+            double* yp = ypart + (ch * 16 + warp) * 4;
+            yp[0] = s0; yp[1] = s1; yp[2] = s2; yp[3] = s3;
+          }
+        }
+      } else {
       if (kact > 0 && len > 0) {
         nseg = 16 / gcd16(kact);
         while (nseg > 1 && len / nseg < 128) nseg >>= 1;
@@ -231,15 +306,27 @@ __global__ void __launch_bounds__(kPT, 1) tridiag_panel_kernel(const __grid_cons
           yp[0] = s0; yp[1] = s1; yp[2] = s2; yp[3] = s3;
         }
       }
+      }
       __syncthreads();
+      double yvp = 0.0;   // this thread's share of y.v
       if (tid < S) {
         const int ch = (tid >> 2) - lq0, r = row_of_slot(tid);
         double s = 0.0;
-        if (ch >= 0 && ch < kact && r > j && r < n)
+        if (ch >= 0 && ch < kact && r > j && r < n) {
           for (int q = 0; q < nseg; ++q) s += ypart[(ch * 16 + q) * 4 + (tid & 3)];
+          if (sym && (n & 1) && r == n - 1) s = fma(a.A[(size_t)r * ld + r], vs[r], s);  // diagonal outside the double2 range
+        }
         ys[tid] = s;
+        yvp = s * vown[tid];
       }
-      __syncthreads();
+      if (sym) {  // publish the column part of this CTA
+        double* zrow = a.Z + (size_t)b * ld;
+        for (int c = j + 1 + tid; c < n; c += kPT) {
+          const double z = zs[c];
+          zrow[c] = z;
+          yvp = fma(z, vs[c], yvp);
+        }
+      }
       // partial dots with the panel vectors, y.v, and y at the next pivot row
       if (tid < 2 * i) {
         const double* arr = tid < i ? own_v : own_w;
@@ -248,15 +335,34 @@ __global__ void __launch_bounds__(kPT, 1) tridiag_panel_kernel(const __grid_cons
         for (int q = 0; q < S; ++q) s = fma(arr[q * ldo + k], vown[q], s);
         a.part[(size_t)((tid < i ? 0 : nb) + k) * G + b] = s;
       }
-      if (warp == kPW - 1) {
-        double s = 0.0;
-        for (int q = lane; q < S; q += 32) s = fma(ys[q], vown[q], s);
-        s = wsum_(s);
-        if (lane == 0) a.part[(size_t)(2 * nb) * G + b] = s;
-      }
+      yvp = bsum_(yvp, red);
+      if (tid == 0) a.part[(size_t)(2 * nb) * G + b] = yvp;
       if (tid < S && row_of_slot(tid) == j + 1) a.part[(size_t)(2 * nb + 1) * G] = ys[tid];
       grid_sync(a.bar, target);
       // ---------------- phase B: reduce the partials ----------------
+      if (sym) {
+        // y on the rows of this CTA += column parts of all CTAs (8 lanes per row, fixed order)
+        for (int base = 0; base < S; base += kPT / 8) {
+          const int sl = base + (tid >> 3), kp = tid & 7;
+          double zsum = 0.0;
+          const int r = sl < S ? row_of_slot(sl) : n;
+          if (r > j && r < n) {
+#pragma unroll 4
+            for (int bb = kp; bb < G; bb += 8) zsum += __ldcg(a.Z + (size_t)bb * ld + r);
+          }
+#pragma unroll
+          for (int o = 4; o > 0; o >>= 1) zsum += __shfl_xor_sync(0xffffffffu, zsum, o);
+          if (kp == 0 && sl < S) ys[sl] += zsum;
+        }
+        if (warp == kPW - 2) {  // column parts of the next pivot row
+          double zsum = 0.0;
+          for (int bb = lane; bb < G; bb += 32) zsum += __ldcg(a.Z + (size_t)bb * ld + j + 1);
+          zsum = wsum_(zsum);
+          if (lane == 0) red[42] = zsum;
+        }
+      } else if (tid == 0) {
+        red[42] = 0.0;
+      }
       const int nred = 2 * i + 1;
       {  // all loads of a warp are issued before the first reduction (one L2 round trip instead of nred / 16)
         constexpr int kU = 9, kQ = 5;  // 2 * 64 + 1 values over 16 warps; up to 160 CTAs
@@ -301,7 +407,7 @@ __global__ void __launch_bounds__(kPT, 1) tridiag_panel_kernel(const __grid_cons
       }
       if (b == 0 && tid <= nb) { a.vrows[(size_t)i * ldo + tid] = 0.0; a.wrows[(size_t)i * ldo + tid] = 0.0; }
       if (tid < S) { vown[tid] = 0.0; ys[tid] = 0.0; }
-      if (tid == 0) { red[40] = 0.0; red[41] = 0.0; }
+      if (tid == 0) { red[40] = 0.0; red[41] = 0.0; red[42] = 0.0; }
     }
     __syncthreads();
     // scalars of the column (every thread, from shared memory)
@@ -312,7 +418,7 @@ __global__ void __launch_bounds__(kPT, 1) tridiag_panel_kernel(const __grid_cons
       c1 = fma(rowW[k], PV[k], c1);
     }
     const double pv = have ? tau_j * (red[40] - 2.0 * pvdot) : 0.0;   // p.v with p = tau * (corrected y)
-    const double w1 = have ? tau_j * (red[41] - c1) - 0.5 * tau_j * pv : 0.0;  // w at the next pivot row
+    const double w1 = have ? tau_j * (red[41] + red[42] - c1) - 0.5 * tau_j * pv : 0.0;  // w at the next pivot row
     // w on the rows of this CTA and the next pivot row, 8 lanes per slot
     double sg2 = 0.0;
     for (int base = 0; base < S; base += kPT / 8) {
@@ -478,6 +584,7 @@ size_t al256(size_t x) { return (x + 255) / 256 * 256; }
 struct BlockedPlan {
   int nb = 0, S = 0, grid = 0;
   size_t smem = 0;
+  bool sym = false;   // room for the column-part accumulator of the symmetric mat-vec
 };
 
 static bool plan_panel(int n, BlockedPlan* p) {
@@ -494,6 +601,7 @@ static bool plan_panel(int n, BlockedPlan* p) {
     const size_t doubles = (size_t)nv + 2 * (size_t)S * (nb + 1) + 3 * S + 4 * nb + (size_t)S * 16 + 64;
     if (doubles * 8 <= (size_t)max_smem) {
       p->nb = nb; p->S = S; p->grid = G; p->smem = doubles * 8;
+      if (nb == 64 && (doubles + nv) * 8 <= (size_t)max_smem && !getenv("VMCPDE_EIGH_NOSYM")) { p->sym = true; p->smem = (doubles + nv) * 8; }
       return true;
     }
   }
@@ -512,7 +620,8 @@ size_t blocked_tridiag_scratch_bytes(int n, int ld) {
   if (!plan_panel(n, &p)) return 0;
   const int nb = p.nb, G = p.grid;
   return al256((size_t)ld * 8) + al256((size_t)(2 * nb + 2) * G * 8) + al256((size_t)G * 8) +
-         2 * al256((size_t)nb * (nb + 1) * 8) + 2 * al256((size_t)2 * nb * ld * 8) + al256(((size_t)n / nb + 2) * 4);
+         2 * al256((size_t)nb * (nb + 1) * 8) + 2 * al256((size_t)2 * nb * ld * 8) + al256(((size_t)n / nb + 2) * 4) +
+         (p.sym ? al256((size_t)G * ld * 8) : 0);
 }
 
 // launches issued by the two blocked stages (reported through vmcpde_eigh_launch_count)
@@ -545,6 +654,9 @@ int tridiag_blocked(double* A, int n, int ld, double* d, double* e, double* tau,
   const int panels = (n + nb - 1) / nb;
   unsigned* bars = (unsigned*)take(((size_t)panels + 2) * 4);
   VMC_CUDA_CHECK(cudaMemsetAsync(a.acol, 0, (size_t)(wp - (uint8_t*)a.acol), s));
+  a.Z = p.sym ? (double*)take((size_t)G * ld * 8) : nullptr;
+  a.sym_min_m = 1536;
+  if (const char* e_ = getenv("VMCPDE_EIGH_SYM_MIN_M")) a.sym_min_m = atoi(e_);
   VMC_CUDA_CHECK(cudaFuncSetAttribute(tridiag_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   for (int pi = 0; pi < panels; ++pi) {
     a.j0 = pi * nb;
