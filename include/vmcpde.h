@@ -120,13 +120,17 @@ int vmcpde_hessian(const vmcpde_flow* f, const double* theta, const double* x, i
 /* Local sums for mpi.global_mean / global_variance (tdvp.py:37-41, mpi_wrapper.py:129-193):
  * sums[0..3] += sum E, sum |E|, sum E^2, sum logp ; sums[4 + p] += sum_i O[i,p] for p < ldo. */
 int vmcpde_moments1(const double* eloc, const double* logp, const double* O, int64_t n, int64_t ldo,
-                    double* sums, vmcpde_stream stream);
+                    double* sums, void* workspace, size_t workspace_bytes, vmcpde_stream stream);
+/* scratch of vmcpde_moments1 / vmcpde_center_force: one partial row of ldo doubles per block of 512 samples
+ * (the column sums are reduced in two fixed-order levels, so results do not depend on the device) */
+int vmcpde_moments_workspace_bytes(int64_t n, int64_t ldo, size_t* bytes);
 /* tdvp.py:40-45 on one chunk: O[i,:] -= meanO (in place); dE[i] = E[i] - meanE; Fsum[p] += sum_i dE[i]*O[i,p];
  * wE[i] = dE[i]^2, wLp[i] = logp[i]^2 (row weights for the SNR covariance and SExp Grams);
  * var_sum[0] += sum_i dE[i]^2.  meanO, Fsum have ldo entries. */
 int vmcpde_center_force(double* O, int64_t n, int64_t ldo, const double* meanO, const double* eloc,
                         const double* logp, double meanE, double* dE, double* wE, double* wLp,
-                        double* Fsum, double* var_sum, vmcpde_stream stream);
+                        double* Fsum, double* var_sum, void* workspace, size_t workspace_bytes,
+                        vmcpde_stream stream);
 /* Weighted Gram accumulation on FP64 tensor cores (DMMA), replacing mpi.global_covariance /
  * _cov_helper_without_p (mpi_wrapper.py:21-25,248-274; tdvp.py:46-47,68-70):
  * for m < n_mats:  S[m][a,b] += sum_i w[m][i] * O[i,a] * O[i,b]   for the tiles of the UPPER triangle.
@@ -160,6 +164,12 @@ int vmcpde_dmma_peak(double* tflops_out);
 int vmcpde_eigh_workspace_bytes(int32_t n, int32_t ld, size_t* bytes);
 int vmcpde_eigh(double* S, int32_t n, int32_t ld, double* ev, double* VT, void* workspace,
                 size_t workspace_bytes, vmcpde_stream stream);
+/* Same decomposition, but only the eigenvectors [col0, col0 + ncols) are back-transformed and written (rows col0..
+ * of VT; other rows untouched) -- the slice one rank of a multi-GPU solve needs (tdvp.py:61-71 sharded over the
+ * eigenvector index).  col0, ncols: multiples of 128 inside the padded size on the blocked path; the unblocked path
+ * writes every row. */
+int vmcpde_eigh_cols(double* S, int32_t n, int32_t ld, double* ev, double* VT, int32_t col0, int32_t ncols,
+                     void* workspace, size_t workspace_bytes, vmcpde_stream stream);
 /* number of kernel launches one vmcpde_eigh(n, ld) call issues */
 int vmcpde_eigh_launch_count(int32_t n, int32_t ld, int32_t* count);
 /* Everything after eigh in TDVP.transform_to_eigenbasis / TDVP.solve (tdvp.py:66-94): VtF = V^T F;
@@ -173,6 +183,15 @@ int vmcpde_solve_tail(const double* ev, const double* VT, int32_t n, int32_t ld,
                       double snrTol, int32_t useSNR, double meanE2, double* VtF, double* rhoVar, double* snr,
                       double* invEv, double* update, double* scalars, void* workspace,
                       size_t workspace_bytes, vmcpde_stream stream);
+/* Eigenvector-local part of the above for the eigenvectors [row0, row0 + nrows) (multiples of 128 when CEO is
+ * given): VtF, rhoVar, snr, invEv on that range (entries outside are not written) and
+ * update_partial[n] = sum_{k in range} V[:,k] invEv_k reg_k VtF_k.  Ranks of a multi-GPU solve each take a slice and
+ * sum the partial updates with one all-reduce; vmcpde_solve_scalars then gives residual and TDVP error. */
+int vmcpde_solve_tail_range(const double* ev, const double* VT, int32_t n, int32_t ld, const double* F,
+                            const double* CEO, double n_glob, double svdTol, double snrTol, int32_t useSNR,
+                            int32_t row0, int32_t nrows, double* VtF, double* rhoVar, double* snr, double* invEv,
+                            double* update_partial, void* workspace, size_t workspace_bytes,
+                            vmcpde_stream stream);
 /* Blocked Cholesky solve S x = F for a shifted, positive definite S (diagonalShift > 0).  S is overwritten
  * by its lower factor.  *info (device int, zero on entry) = 1 + index of the first non-positive pivot. */
 int vmcpde_chol_solve(double* S, int32_t n, int32_t ld, const double* F, double* x, int32_t* info,

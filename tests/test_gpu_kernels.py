@@ -105,14 +105,15 @@ def test_sampler_local_terms_moments_gram(L, d, depth, h, variant, latent, eqnam
     # ---- first moments, centring, force, three weighted Grams (tdvp.py:36-52, 68-70)
     T = tdvp.OracleTDVP(); T.solve(Eo.numpy(), Oo.numpy(), lpo2.numpy())
     sums = torch.zeros(4 + Pp, device=dev(), dtype=f64)
-    _lib.check(L.vmcpde_moments1(_lib.ptr(E), _lib.ptr(lp2), _lib.ptr(O), n, Pp, _lib.ptr(sums), _lib.stream()))
+    mws = torch.empty(((n + 511) // 512 + 1) * Pp, device=O.device, dtype=torch.float64)
+    _lib.check(L.vmcpde_moments1(_lib.ptr(E), _lib.ptr(lp2), _lib.ptr(O), n, Pp, _lib.ptr(sums), _lib.ptr(mws), mws.numel() * 8, _lib.stream()))
     assert abs(float(sums[0]) / n - T.ElocMean) <= 1e-11 * (abs(T.ElocMean) + np.abs(Eo.numpy()).max())
     assert abs(float(sums[1]) / n - T.ElocMeanAbs) <= 1e-11 * T.ElocMeanAbs
     assert relerr(sums[4:4 + P] / n, T.gradMean) < 1e-10
     meanO = (sums[4:] / n).contiguous()
     dE = torch.zeros(nrow, device=dev(), dtype=f64); wE = torch.zeros_like(dE); wLp = torch.zeros_like(dE)
     F = torch.zeros(Pp, device=dev(), dtype=f64); var = torch.zeros(1, device=dev(), dtype=f64)
-    _lib.check(L.vmcpde_center_force(_lib.ptr(O), n, Pp, _lib.ptr(meanO), _lib.ptr(E), _lib.ptr(lp2), float(sums[0]) / n, _lib.ptr(dE), _lib.ptr(wE), _lib.ptr(wLp), _lib.ptr(F), _lib.ptr(var), _lib.stream()))
+    _lib.check(L.vmcpde_center_force(_lib.ptr(O), n, Pp, _lib.ptr(meanO), _lib.ptr(E), _lib.ptr(lp2), float(sums[0]) / n, _lib.ptr(dE), _lib.ptr(wE), _lib.ptr(wLp), _lib.ptr(F), _lib.ptr(var), _lib.ptr(mws), mws.numel() * 8, _lib.stream()))
     assert relerr(F[:P] / n, T.F0) < 1e-10 and abs(float(var) / n / T.ElocVar - 1) < 1e-11
     S = [torch.zeros(Pp, Pp, device=dev(), dtype=f64) for _ in range(3)]
     _lib.check(L.vmcpde_gram(_lib.ptr(O), nrow, Pp, Pp, 3, _lib.ptr_array([None, wLp, wE]), _lib.ptr_array(S), _lib.stream()))

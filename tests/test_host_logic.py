@@ -68,6 +68,32 @@ def test_timings_and_cov_matrix():
     assert np.allclose(S.numpy(), L @ L.T)
 
 
+def test_solve_shard_ranges_partition_the_eigenvectors():
+    """tdvp.solve_shard_range: contiguous 128-blocks, every eigenvector exactly once, and the per-slice partial updates
+    plus zero-padded slice vectors sum to the unsharded solve (the all-reduce pattern of TDVP._finish)."""
+    from vmc_pde_b200.tdvp import solve_shard_range
+    for Pp, R in ((128, 1), (256, 2), (1024, 3), (8192, 8), (16384, 5), (2176, 8)):
+        covered = np.zeros(Pp, dtype=int)
+        for r in range(R):
+            row0, nrows = solve_shard_range(Pp, R, r)
+            assert row0 % 128 == 0 and nrows % 128 == 0 and nrows > 0
+            covered[row0:row0 + nrows] += 1
+        assert (covered == 1).all()
+    rng = np.random.default_rng(5)
+    P, Pp, R = 300, 384, 3
+    A = rng.normal(size=(P + 40, P)); S = A.T @ A / (P + 40); F = rng.normal(size=P)
+    ev, V = np.linalg.eigh(S)
+    coef = (V.T @ F) / ev
+    full = V @ coef
+    acc, vt = np.zeros(P), np.zeros(Pp)
+    for r in range(R):
+        row0, nrows = solve_shard_range(Pp, R, r)
+        k0, k1 = row0, min(P, row0 + nrows)
+        acc += V[:, k0:k1] @ coef[k0:k1]
+        vt[k0:k1] += (V.T @ F)[k0:k1]
+    assert np.allclose(acc, full, rtol=1e-12, atol=1e-12) and np.allclose(vt[:P], V.T @ F)
+
+
 def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 

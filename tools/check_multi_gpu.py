@@ -1,0 +1,48 @@
+"""One TDVP right-hand side at a moderate size, run (a) on 1 rank and (b) under torchrun with R ranks; both write their
+results to gpurun_out/ and `--compare` checks that the sharded run (samples AND the post-tridiagonal solve sharded)
+reproduces the single-rank one.  usage (on a multi-GPU box):
+    python tools/check_multi_gpu.py --out gpurun_out/mg_1.pt
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/check_multi_gpu.py --out gpurun_out/mg_2.pt
+    python tools/check_multi_gpu.py --compare gpurun_out/mg_1.pt gpurun_out/mg_2.pt"""
+import argparse, os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+ap = argparse.ArgumentParser()
+ap.add_argument("--out"); ap.add_argument("--compare", nargs=2)
+args = ap.parse_args()
+if args.compare:
+    a, b = torch.load(args.compare[0]), torch.load(args.compare[1])
+    rel = lambda x, y: float((x - y).abs().max() / y.abs().max())
+    S0 = a["S0"]
+    du = b["update"] - a["update"]
+    print("S0", rel(b["S0"], a["S0"]), "F0", rel(b["F0"], a["F0"]), "ev", rel(b["ev"], a["ev"]), "VtF^2", rel(b["VtF"] ** 2, a["VtF"] ** 2))
+    big = (a["ev"] / a["ev"][-1]).abs() > 1e-8
+    print("snr(big)", float((b["snr"][big] / a["snr"][big] - 1).abs().max()), "residual", float(a["res"]), float(b["res"]),
+          "tdvp_error", float(a["err"]), float(b["err"]))
+    sn = float(du @ S0 @ du) / float(a["update"] @ S0 @ a["update"])
+    print("update S-norm rel diff", sn)
+    Va, Vb = a["V"], b["V"]
+    print("|S V - V ev| (sharded V)", float((S0 @ Vb - Vb * b["ev"]).abs().max() / a["ev"][-1]))
+    ok = rel(b["S0"], a["S0"]) < 1e-11 and rel(b["ev"], a["ev"]) < 1e-11 and sn < 1e-14 and abs(float(a["err"]) - float(b["err"])) < 1e-10
+    print("MULTI-GPU CHECK", "OK" if ok else "FAILED")
+    sys.exit(0 if ok else 1)
+import torch.distributed as dist
+world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+if world > 1:
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+from vmc_pde_b200 import sampler, var_state, evolutionEq, tdvp
+d, depth, h, N = 2, 4, 85, 2 ** 14           # BASELINE config C2 architecture (P = 2053)
+off = np.zeros(d)
+smp = sampler.Sampler(dim=d, numChains=30, name="Gauss", mcmc_info={"offset": off, "bound": 0.25})
+vs = var_state.VarState(smp, d, 1, depth, network_args={"intmediate": (h,), "offset": off, "latentSpaceName": "Gauss", "dim": d})
+eq = evolutionEq.EvolutionEquation(dim=d, name="diffusion")
+T = tdvp.TDVP()
+upd, info = T(vs.get_parameters(), 0.0, psi=vs, evolutionEq=eq, nSamplesTDVP=N, nSamplesObs=N, timings=None)
+V = T.V   # collective when sharded
+if rank == 0:
+    torch.save({"update": upd.cpu(), "S0": T.S0.cpu(), "F0": T.F0.cpu(), "ev": T.ev.cpu(), "VtF": T.VtF.cpu(), "snr": T.snr.cpu(),
+                "res": T.solverResidual.cpu(), "err": T.tdvp_error.cpu(), "V": V.cpu(), "entropy": info["entropy"].cpu()}, args.out)
+    print("rank 0 wrote", args.out, "P", vs.numParameters, "world", world, flush=True)
+if world > 1:
+    dist.barrier(); dist.destroy_process_group()

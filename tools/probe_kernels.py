@@ -56,14 +56,15 @@ def case(d, depth, h, variant, latent, eqname, n):
     e["H"] = err(H.cpu(), st.hessian(xo[:64]))
     # moments / centre / gram
     sums = torch.zeros(4 + Pp, device=dev, dtype=torch.float64)
-    _lib.check(L.vmcpde_moments1(_lib.ptr(E), _lib.ptr(lp2), _lib.ptr(O), n, Pp, _lib.ptr(sums), _lib.stream()))
+    mws = torch.empty(((n + 511) // 512 + 1) * Pp, device=O.device, dtype=torch.float64)
+    _lib.check(L.vmcpde_moments1(_lib.ptr(E), _lib.ptr(lp2), _lib.ptr(O), n, Pp, _lib.ptr(sums), _lib.ptr(mws), mws.numel() * 8, _lib.stream()))
     T = tdvp.OracleTDVP(); T.solve(Eo.numpy(), Oo.numpy(), lpo2.numpy())
     e["meanE"] = abs(float(sums[0]) / n - T.ElocMean) / (abs(T.ElocMean) + 1e-300)
     e["meanO"] = err((sums[4:4 + P] / n).cpu(), T.gradMean)
     meanO = (sums[4:] / n).contiguous()
     dE = torch.zeros(nrow, device=dev, dtype=torch.float64); wE = torch.zeros_like(dE); wLp = torch.zeros_like(dE)
     F = torch.zeros(Pp, device=dev, dtype=torch.float64); var = torch.zeros(1, device=dev, dtype=torch.float64)
-    _lib.check(L.vmcpde_center_force(_lib.ptr(O), n, Pp, _lib.ptr(meanO), _lib.ptr(E), _lib.ptr(lp2), float(sums[0]) / n, _lib.ptr(dE), _lib.ptr(wE), _lib.ptr(wLp), _lib.ptr(F), _lib.ptr(var), _lib.stream()))
+    _lib.check(L.vmcpde_center_force(_lib.ptr(O), n, Pp, _lib.ptr(meanO), _lib.ptr(E), _lib.ptr(lp2), float(sums[0]) / n, _lib.ptr(dE), _lib.ptr(wE), _lib.ptr(wLp), _lib.ptr(F), _lib.ptr(var), _lib.ptr(mws), mws.numel() * 8, _lib.stream()))
     e["F"] = err((F[:P] / n).cpu(), T.F0); e["var"] = abs(float(var) / n - T.ElocVar) / T.ElocVar
     S = [torch.zeros(Pp, Pp, device=dev, dtype=torch.float64) for _ in range(3)]
     _lib.check(L.vmcpde_gram(_lib.ptr(O), nrow, Pp, Pp, 3, _lib.ptr_array([None, wLp, wE]), _lib.ptr_array(S), _lib.stream()))

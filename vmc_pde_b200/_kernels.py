@@ -146,16 +146,35 @@ def local_terms(flow, theta, x, eq, O=None, ldo=0, want=("eloc", "logp", "grad",
     return out
 
 
+_mom_ws = {}
+
+
+def _moments_ws(n, ldo):
+    """Grow-only scratch of the two-level column reductions (one partial row per 512 samples)."""
+    nb = C.c_size_t(0)
+    _lib.check(_lib.load().vmcpde_moments_workspace_bytes(int(n), int(ldo), C.byref(nb)))
+    dev = _dev()
+    cur = _mom_ws.get(dev)
+    if cur is None or cur.numel() * 8 < nb.value:
+        _mom_ws[dev] = None
+        cur = torch.empty(nb.value // 8 + 2, dtype=f64, device=dev)
+        _mom_ws[dev] = cur
+    return cur
+
+
 def moments1(eloc, logp_, O, n, ldo, sums):
-    _count(1)
-    _lib.check(_lib.load().vmcpde_moments1(_lib.ptr(eloc), _lib.ptr(logp_), _lib.ptr(O), int(n), int(ldo), _lib.ptr(sums), _lib.stream()))
+    _count(3 if O is not None else 1)
+    ws = _moments_ws(n, ldo)
+    _lib.check(_lib.load().vmcpde_moments1(_lib.ptr(eloc), _lib.ptr(logp_), _lib.ptr(O), int(n), int(ldo), _lib.ptr(sums),
+                                           _lib.ptr(ws), ws.numel() * 8, _lib.stream()))
 
 
 def center_force(O, n, ldo, meanO, eloc, logp_, meanE, dE, wE, wLp, Fsum, var_sum):
-    _count(1)
+    _count(3)
+    ws = _moments_ws(n, ldo)
     _lib.check(_lib.load().vmcpde_center_force(_lib.ptr(O), int(n), int(ldo), _lib.ptr(meanO), _lib.ptr(eloc), _lib.ptr(logp_),
                                                float(meanE), _lib.ptr(dE), _lib.ptr(wE), _lib.ptr(wLp), _lib.ptr(Fsum),
-                                               _lib.ptr(var_sum), _lib.stream()))
+                                               _lib.ptr(var_sum), _lib.ptr(ws), ws.numel() * 8, _lib.stream()))
 
 
 def gram(O, n, ldo, Pp, weights, mats):
@@ -216,6 +235,22 @@ def eigh(A_destroyed, n, ld, ev, VT, ws):
     _count(eigh_launch_count(n, ld))
     _lib.check(_lib.load().vmcpde_eigh(_lib.ptr(A_destroyed), int(n), int(ld), _lib.ptr(ev), _lib.ptr(VT), _lib.ptr(ws),
                                        ws.numel(), _lib.stream()))
+
+
+def eigh_cols(A_destroyed, n, ld, ev, VT, col0, ncols, ws):
+    """Eigen-decomposition with only the eigenvectors [col0, col0 + ncols) back-transformed (rows of VT)."""
+    _count(eigh_launch_count(n, ld))
+    _lib.check(_lib.load().vmcpde_eigh_cols(_lib.ptr(A_destroyed), int(n), int(ld), _lib.ptr(ev), _lib.ptr(VT), int(col0),
+                                            int(ncols), _lib.ptr(ws), ws.numel(), _lib.stream()))
+
+
+def solve_tail_range(ev, VT, n, ld, F, CEO, n_glob, svdTol, snrTol, useSNR, row0, nrows, VtF, rhoVar, snr, invEv,
+                     update_partial, ws):
+    _count(6 if CEO is not None else 3)
+    _lib.check(_lib.load().vmcpde_solve_tail_range(_lib.ptr(ev), _lib.ptr(VT), int(n), int(ld), _lib.ptr(F), _lib.ptr(CEO),
+                                                   float(n_glob), float(svdTol), float(snrTol), int(bool(useSNR)), int(row0),
+                                                   int(nrows), _lib.ptr(VtF), _lib.ptr(rhoVar), _lib.ptr(snr), _lib.ptr(invEv),
+                                                   _lib.ptr(update_partial), _lib.ptr(ws), ws.numel(), _lib.stream()))
 
 
 def solve_tail(ev, VT, n, ld, F, S, S0, CEO, n_glob, svdTol, snrTol, useSNR, meanE2, VtF, rhoVar, snr, invEv, update,

@@ -30,8 +30,9 @@ SIGNATURES = {
     "vmcpde_local_terms": (C.c_int, [_vp, _vp, _vp, _i64, C.POINTER(Equation), _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "vmcpde_flow_transform": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "vmcpde_hessian": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
-    "vmcpde_moments1": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp]),
-    "vmcpde_center_force": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _dbl, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vmcpde_moments_workspace_bytes": (C.c_int, [_i64, _i64, C.POINTER(C.c_size_t)]),
+    "vmcpde_moments1": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, C.c_size_t, _vp]),
+    "vmcpde_center_force": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _dbl, _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "vmcpde_gram": (C.c_int, [_vp, _i64, _i64, _i32, _i32, C.POINTER(_vp), C.POINTER(_vp), _vp]),
     "vmcpde_sym_finalize": (C.c_int, [_vp, _i32, _dbl, _vp]),
     "vmcpde_diag_shift": (C.c_int, [_vp, _vp, _i32, _i32, _dbl, _vp]),
@@ -39,6 +40,9 @@ SIGNATURES = {
     "vmcpde_gemm_tn": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i64, _dbl, _dbl, _vp]),
     "vmcpde_eigh_workspace_bytes": (C.c_int, [_i32, _i32, C.POINTER(C.c_size_t)]),
     "vmcpde_eigh": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "vmcpde_eigh_cols": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _i32, _i32, _vp, C.c_size_t, _vp]),
+    "vmcpde_solve_tail_range": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _dbl, _dbl, _dbl, _i32, _i32, _i32,
+                                          _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "vmcpde_eigh_launch_count": (C.c_int, [_i32, _i32, C.POINTER(_i32)]),
     "vmcpde_solve_tail_workspace_bytes": (C.c_int, [_i32, _i32, C.POINTER(C.c_size_t)]),
     "vmcpde_solve_tail": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _dbl, _dbl, _dbl, _i32, _dbl,

@@ -620,7 +620,7 @@ int blocked_backtransform_launches(int n);
 int tridiag_blocked(double* A, int n, int ld, double* d, double* e, double* tau, void* scratch, size_t scratch_bytes,
                     cudaStream_t s);
 int backtransform_blocked(double* A, const double* tau, int n, int ld, const double* ZT, double* Zn, double* AT,
-                          void* scratch, size_t scratch_bytes, double* VT, cudaStream_t s);
+                          void* scratch, size_t scratch_bytes, double* VT, int col0, int ncols, cudaStream_t s);
 
 }  // namespace vmc
 
@@ -653,9 +653,8 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_eigh_launch_count(i
 
 // S (n x n, leading dimension ld, full symmetric) is destroyed.  ev[n] ascending; VT row k = eigenvector k.
 // Replaces np.linalg.eigh at tdvp.py:61-64.
-extern "C" __attribute__((visibility("default"))) int vmcpde_eigh(double* S, int32_t n, int32_t ld, double* ev, double* VT,
-                                                                 void* workspace, size_t workspace_bytes,
-                                                                 vmcpde_stream stream) {
+static int eigh_impl(double* S, int32_t n, int32_t ld, double* ev, double* VT, int32_t col0, int32_t ncols, void* workspace,
+                     size_t workspace_bytes, vmcpde_stream stream) {
   VMC_REQUIRE(S && ev && VT && workspace, "vmcpde_eigh: null pointer");
   VMC_REQUIRE(n >= 1 && ld >= n, "vmcpde_eigh: bad dimensions");
   size_t need = 0;
@@ -756,7 +755,9 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_eigh(double* S, int
   const double* ZT = b.QT;
   if (blocked) {
     // Zn = ZT^T lives in U, the reflector transpose in the free ping buffer; VT may alias either source
-    if (int rc = backtransform_blocked(S, tau, n, ld, ZT, U, b.QT_new, bt_scratch, bt_bytes, VT, s)) return rc;
+    const int np = (n + 127) / 128 * 128;
+    if (ncols <= 0) { col0 = 0; ncols = np; }
+    if (int rc = backtransform_blocked(S, tau, n, ld, ZT, U, b.QT_new, bt_scratch, bt_bytes, VT, col0, ncols, s)) return rc;
   } else if (ZT == VT) {
     VMC_CUDA_CHECK(cudaMemcpyAsync(QTb, VT, (size_t)n * ld * 8, cudaMemcpyDeviceToDevice, s));
     ZT = QTb;
@@ -788,4 +789,20 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_eigh(double* S, int
     for (auto& e_ : evt) cudaEventDestroy(e_);
   }
   return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int vmcpde_eigh(double* S, int32_t n, int32_t ld, double* ev, double* VT,
+                                                                 void* workspace, size_t workspace_bytes,
+                                                                 vmcpde_stream stream) {
+  return eigh_impl(S, n, ld, ev, VT, 0, 0, workspace, workspace_bytes, stream);
+}
+
+// Same decomposition, but only the eigenvectors [col0, col0 + ncols) are back-transformed and written (rows col0.. of VT;
+// the other rows are left untouched): the slice one rank of a multi-GPU solve needs.  col0 and ncols are multiples of 128
+// inside the padded size when the blocked path runs (n >= 384, padded ld); the unblocked path writes every row.
+extern "C" __attribute__((visibility("default"))) int vmcpde_eigh_cols(double* S, int32_t n, int32_t ld, double* ev, double* VT,
+                                                                      int32_t col0, int32_t ncols, void* workspace,
+                                                                      size_t workspace_bytes, vmcpde_stream stream) {
+  VMC_REQUIRE(col0 >= 0 && ncols > 0, "vmcpde_eigh_cols: bad eigenvector range");
+  return eigh_impl(S, n, ld, ev, VT, col0, ncols, workspace, workspace_bytes, stream);
 }

@@ -486,6 +486,16 @@ __global__ void __launch_bounds__(256) transpose_sq_kernel(const double* __restr
   for (int r = ty; r < 32; r += 8) B[(size_t)(c0 + r) * ld + r0 + tx] = tile[tx][r];
 }
 
+// B[c0 + c][r] = A[r][c0 + c] for r < rows, c < cols (multiples of 32): columns [c0, c0 + cols) of A become rows of B
+__global__ void __launch_bounds__(256) transpose_cols_kernel(const double* __restrict__ A, double* __restrict__ B, int ld, int c0) {
+  __shared__ double tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int r0 = blockIdx.y * 32, cc = c0 + blockIdx.x * 32;
+  for (int r = ty; r < 32; r += 8) tile[r][tx] = A[(size_t)(r0 + r) * ld + cc + tx];
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) B[(size_t)(cc + r) * ld + r0 + tx] = tile[tx][r];
+}
+
 // Partial Gram of one 128-reflector block over a slice of 1024 coordinates:
 // part[blk][slice][k][k'] = sum_{c in slice} AT[c][128 blk + k] AT[c][128 blk + k']   (DMMA, 8 warps x 64x32)
 constexpr int kBK = 128;       // reflectors per back-transform block
@@ -684,12 +694,15 @@ size_t blocked_backtransform_scratch_bytes(int n, int ld) {
 
 // V = H_0 ... H_{n-3} Z.  ZT (np x ld, rows = eigenvectors of the tridiagonal, zero padded) is consumed;
 // A holds the reflectors (row convention) and is masked in place; AT and Zn are np x ld work matrices;
-// `scratch` may alias ZT (it is dead once Zn = ZT^T has been formed).  VT (rows = eigenvectors) may alias ZT or AT.
+// VT (rows = eigenvectors) may alias ZT or AT.  Only the eigenvectors [col0, col0 + ncols) (multiples of 128) are
+// transformed and written (rows col0.. of VT): ranks of a multi-GPU solve each take a slice.
 int backtransform_blocked(double* A, const double* tau, int n, int ld, const double* ZT, double* Zn, double* AT,
-                          void* scratch, size_t scratch_bytes, double* VT, cudaStream_t s) {
+                          void* scratch, size_t scratch_bytes, double* VT, int col0, int ncols, cudaStream_t s) {
   const int np = (n + 127) / 128 * 128, nblk = np / kBK;
   const int max_slices = (np + kSlice - 1) / kSlice;
   if (scratch_bytes < blocked_backtransform_scratch_bytes(n, ld)) return set_error(VMCPDE_EINVAL, "backtransform_blocked: scratch too small");
+  if (col0 < 0 || ncols <= 0 || col0 % 128 || ncols % 128 || col0 + ncols > np)
+    return set_error(VMCPDE_EINVAL, "backtransform_blocked: eigenvector range must be 128-aligned inside the padded size");
   const dim3 tgrid(np / 32, np / 32);
   transpose_sq_kernel<<<tgrid, 256, 0, s>>>(ZT, Zn, ld);
   mask_transpose_kernel<<<tgrid, 256, 0, s>>>(A, AT, ld, n);
@@ -704,16 +717,17 @@ int backtransform_blocked(double* A, const double* tau, int n, int ld, const dou
   VMC_CUDA_CHECK(cudaFuncSetAttribute(larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
   larft_kernel<<<nblk, 128, lsm, s>>>(part, max_slices, np, tau, n, Tt);
   VMC_LAUNCH_CHECK("backtransform_blocked setup");
+  double* Zc = Zn + col0;
   for (int blk = nblk - 1; blk >= 0; --blk) {
     const int c0 = blk * kBK, K = np - c0;
-    // G1 = Y^T Zn  (128 x np), contraction over the coordinates c >= c0
-    if (int rc = vmcpde_gemm_tn(AT + (size_t)c0 * ld + c0, ld, Zn + (size_t)c0 * ld, ld, G1, ld, kBK, np, K, 1.0, 0.0, (vmcpde_stream)s)) return rc;
+    // G1 = Y^T Zn  (128 x ncols), contraction over the coordinates c >= c0
+    if (int rc = vmcpde_gemm_tn(AT + (size_t)c0 * ld + c0, ld, Zc + (size_t)c0 * ld, ld, G1, ld, kBK, ncols, K, 1.0, 0.0, (vmcpde_stream)s)) return rc;
     // G2 = T G1
-    if (int rc = vmcpde_gemm_tn(Tt + (size_t)blk * kBK * kBK, kBK, G1, ld, G2, ld, kBK, np, kBK, 1.0, 0.0, (vmcpde_stream)s)) return rc;
-    // Zn[c0:, :] -= Y G2
-    if (int rc = vmcpde_gemm_tn(A + (size_t)c0 * ld + c0, ld, G2, ld, Zn + (size_t)c0 * ld, ld, K, np, kBK, -1.0, 1.0, (vmcpde_stream)s)) return rc;
+    if (int rc = vmcpde_gemm_tn(Tt + (size_t)blk * kBK * kBK, kBK, G1, ld, G2, ld, kBK, ncols, kBK, 1.0, 0.0, (vmcpde_stream)s)) return rc;
+    // Zn[c0:, range] -= Y G2
+    if (int rc = vmcpde_gemm_tn(A + (size_t)c0 * ld + c0, ld, G2, ld, Zc + (size_t)c0 * ld, ld, K, ncols, kBK, -1.0, 1.0, (vmcpde_stream)s)) return rc;
   }
-  transpose_sq_kernel<<<tgrid, 256, 0, s>>>(Zn, VT, ld);
+  transpose_cols_kernel<<<dim3(ncols / 32, np / 32), 256, 0, s>>>(Zn, VT, ld, col0);
   VMC_LAUNCH_CHECK("backtransform_blocked");
   return 0;
 }

@@ -2,12 +2,15 @@
 // Replaces the reference's tiny pmaps and host-staged reductions: tdvp.py:28-33,37-45,50-51 and
 // mpi_wrapper.py:129-245 (local part; the cross-rank sum is one NCCL allreduce of the packed buffer).
 // All reductions are single-writer and fixed-order, so results are run-to-run deterministic.
+#include <cstdint>
 #include "common.cuh"
 
 namespace vmc {
 
-constexpr int kColThreads = 256;   // 8 warps; lane <-> column, warps stride over rows
-constexpr int kColsPerCta = 32;
+constexpr int kRT = 256;                 // threads per CTA
+constexpr int kKC = 8;                   // double2 per thread and row: a CTA covers 2 * kRT * kKC = 4096 columns
+constexpr int kTileCols = 2 * kRT * kKC;
+constexpr int kRowsPerCta = 512;         // fixed, so that the summation order does not depend on the device
 
 __device__ __forceinline__ double block_reduce_sum(double v, double* sh) {
 #pragma unroll
@@ -23,97 +26,114 @@ __device__ __forceinline__ double block_reduce_sum(double v, double* sh) {
   return r;  // valid on thread 0
 }
 
-// sums[4 + c] += sum_i O[i][c] ; last CTA: sums[0..3] += (sum E, sum|E|, sum E^2, sum logp)
-__global__ void __launch_bounds__(kColThreads)
-moments1_kernel(const double* __restrict__ eloc, const double* __restrict__ logp, const double* __restrict__ O,
-                long long n, long long ldo, double* __restrict__ sums, int col_ctas) {
-  __shared__ double sh[8][kColsPerCta + 1];
-  __shared__ double shs[8];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if ((int)blockIdx.x < col_ctas) {
-    const long long c = (long long)blockIdx.x * kColsPerCta + lane;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    if (c < ldo) {
-      long long i = warp;
-      for (; i + 24 < n; i += 32) {
-        a0 += O[i * ldo + c];
-        a1 += O[(i + 8) * ldo + c];
-        a2 += O[(i + 16) * ldo + c];
-        a3 += O[(i + 24) * ldo + c];
-      }
-      for (; i < n; i += 8) a0 += O[i * ldo + c];
-    }
-    sh[warp][lane] = (a0 + a1) + (a2 + a3);
-    __syncthreads();
-    if (warp == 0 && c < ldo) {
-      double s = 0.0;
+// Row-block streaming pass over O (every row is read as one contiguous run: HBM-friendly), two-level fixed-order
+// reduction:  CENTER = false:  part[rb][c] = sum_{i in block rb} O[i][c]
+//             CENTER = true :  O[i][c] -= meanO[c];  part[rb][c] = sum_{i in block rb} (E[i] - meanE) * O[i][c]
+// grid = (column tiles of 4096, row blocks of 512); ldo must be even.
+template <bool CENTER>
+__global__ void __launch_bounds__(kRT)
+rowblock_kernel(double* __restrict__ O, long long n, long long ldo, const double* __restrict__ meanO,
+                const double* __restrict__ eloc, double meanE, double* __restrict__ part) {
+  const long long c0 = (long long)blockIdx.x * kTileCols + 2 * threadIdx.x;
+  const long long i0 = (long long)blockIdx.y * kRowsPerCta;
+  const long long i1 = min(n, i0 + kRowsPerCta);
+  double2 acc[kKC], mu[kKC];
+  bool in[kKC];
 #pragma unroll
-      for (int w = 0; w < 8; ++w) s += sh[w][lane];
-      sums[4 + c] += s;
-    }
-  } else {
-    double e = 0.0, ea = 0.0, e2 = 0.0, lp = 0.0;
-    for (long long i = threadIdx.x; i < n; i += kColThreads) {
-      const double v = eloc ? eloc[i] : 0.0;
-      e += v; ea += fabs(v); e2 += v * v;
-      lp += logp ? logp[i] : 0.0;
-    }
-    double r;
-    r = block_reduce_sum(e, shs);  if (threadIdx.x == 0) sums[0] += r;
-    r = block_reduce_sum(ea, shs); if (threadIdx.x == 0) sums[1] += r;
-    r = block_reduce_sum(e2, shs); if (threadIdx.x == 0) sums[2] += r;
-    r = block_reduce_sum(lp, shs); if (threadIdx.x == 0) sums[3] += r;
+  for (int k = 0; k < kKC; ++k) {
+    const long long c = c0 + (long long)k * 2 * kRT;
+    in[k] = c < ldo;
+    acc[k] = make_double2(0.0, 0.0);
+    mu[k] = (CENTER && in[k]) ? *(const double2*)(meanO + c) : make_double2(0.0, 0.0);
   }
+  auto load_row = [&](long long i, double2 (&v)[kKC]) {
+    const double* row = O + i * ldo + c0;
+#pragma unroll
+    for (int k = 0; k < kKC; ++k) v[k] = in[k] ? *(const double2*)(row + k * 2 * kRT) : make_double2(0.0, 0.0);
+  };
+  auto use_row = [&](long long i, double2 (&v)[kKC]) {
+    if (CENTER) {
+      double* row = O + i * ldo + c0;
+      const double de = __ldg(eloc + i) - meanE;
+#pragma unroll
+      for (int k = 0; k < kKC; ++k) {
+        v[k].x -= mu[k].x; v[k].y -= mu[k].y;
+        if (in[k]) *(double2*)(row + k * 2 * kRT) = v[k];
+        acc[k].x = fma(de, v[k].x, acc[k].x); acc[k].y = fma(de, v[k].y, acc[k].y);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < kKC; ++k) { acc[k].x += v[k].x; acc[k].y += v[k].y; }
+    }
+  };
+  long long i = i0;
+  for (; !CENTER && i + 1 < i1; i += 2) {  // column sums: two rows (16 x 16 B per thread) in flight; the centring
+                                            // pass keeps one (register pressure costs more than it gains there)
+    double2 va[kKC], vb[kKC];
+    load_row(i, va);
+    load_row(i + 1, vb);
+    use_row(i, va);
+    use_row(i + 1, vb);
+  }
+  for (; i < i1; ++i) {
+    double2 va[kKC];
+    load_row(i, va);
+    use_row(i, va);
+  }
+  double* out = part + (long long)blockIdx.y * ldo + c0;
+#pragma unroll
+  for (int k = 0; k < kKC; ++k)
+    if (in[k]) *(double2*)(out + k * 2 * kRT) = acc[k];
 }
 
-// O[i][c] -= meanO[c];  Fsum[c] += sum_i (E[i]-meanE) * O[i][c];  last CTA writes dE, wE, wLp, var_sum
-__global__ void __launch_bounds__(kColThreads)
-center_force_kernel(double* __restrict__ O, long long n, long long ldo, const double* __restrict__ meanO,
-                    const double* __restrict__ eloc, const double* __restrict__ logp, double meanE,
-                    double* __restrict__ dE, double* __restrict__ wE, double* __restrict__ wLp,
-                    double* __restrict__ Fsum, double* __restrict__ var_sum, int col_ctas) {
-  __shared__ double sh[8][kColsPerCta + 1];
-  __shared__ double shs[8];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if ((int)blockIdx.x < col_ctas) {
-    const long long c = (long long)blockIdx.x * kColsPerCta + lane;
-    double a0 = 0.0, a1 = 0.0;
-    if (c < ldo) {
-      const double mu = meanO[c];
-      long long i = warp;
-      for (; i + 8 < n; i += 16) {
-        const double v0 = O[i * ldo + c] - mu, v1 = O[(i + 8) * ldo + c] - mu;
-        O[i * ldo + c] = v0;
-        O[(i + 8) * ldo + c] = v1;
-        a0 = fma(eloc[i] - meanE, v0, a0);
-        a1 = fma(eloc[i + 8] - meanE, v1, a1);
-      }
-      for (; i < n; i += 8) {
-        const double v0 = O[i * ldo + c] - mu;
-        O[i * ldo + c] = v0;
-        a0 = fma(eloc[i] - meanE, v0, a0);
-      }
-    }
-    sh[warp][lane] = a0 + a1;
-    __syncthreads();
-    if (warp == 0 && c < ldo) {
-      double s = 0.0;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) s += sh[w][lane];
-      Fsum[c] += s;
-    }
-  } else {
-    double v2 = 0.0;
-    for (long long i = threadIdx.x; i < n; i += kColThreads) {
-      const double d = eloc[i] - meanE;
-      if (dE) dE[i] = d;
-      if (wE) wE[i] = d * d;
-      if (wLp) wLp[i] = logp[i] * logp[i];
-      v2 += d * d;
-    }
-    const double r = block_reduce_sum(v2, shs);
-    if (threadIdx.x == 0 && var_sum) var_sum[0] += r;
+// dst[c] += sum_rb part[rb][c]  (fixed order)
+__global__ void __launch_bounds__(256) colsum_partials_kernel(const double* __restrict__ part, int row_blocks, long long ldo,
+                                                              double* __restrict__ dst) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ldo) return;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int rb = 0;
+  for (; rb + 3 < row_blocks; rb += 4) {
+    s0 += part[(long long)rb * ldo + c]; s1 += part[(long long)(rb + 1) * ldo + c];
+    s2 += part[(long long)(rb + 2) * ldo + c]; s3 += part[(long long)(rb + 3) * ldo + c];
   }
+  for (; rb < row_blocks; ++rb) s0 += part[(long long)rb * ldo + c];
+  dst[c] += (s0 + s1) + (s2 + s3);
+}
+
+// sums[0..3] += (sum E, sum|E|, sum E^2, sum logp)   (one CTA)
+__global__ void __launch_bounds__(1024) scalar_moments_kernel(const double* __restrict__ eloc, const double* __restrict__ logp,
+                                                              long long n, double* __restrict__ sums) {
+  __shared__ double shs[32];
+  double e = 0.0, ea = 0.0, e2 = 0.0, lp = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const double v = eloc ? eloc[i] : 0.0;
+    e += v; ea += fabs(v); e2 += v * v;
+    lp += logp ? logp[i] : 0.0;
+  }
+  double r;
+  r = block_reduce_sum(e, shs);  if (threadIdx.x == 0) sums[0] += r;
+  r = block_reduce_sum(ea, shs); if (threadIdx.x == 0) sums[1] += r;
+  r = block_reduce_sum(e2, shs); if (threadIdx.x == 0) sums[2] += r;
+  r = block_reduce_sum(lp, shs); if (threadIdx.x == 0) sums[3] += r;
+}
+
+// dE, dE^2, logp^2 per sample and var_sum += sum dE^2   (one CTA)
+__global__ void __launch_bounds__(1024) sample_weights_kernel(const double* __restrict__ eloc, const double* __restrict__ logp,
+                                                              long long n, double meanE, double* __restrict__ dE,
+                                                              double* __restrict__ wE, double* __restrict__ wLp,
+                                                              double* __restrict__ var_sum) {
+  __shared__ double shs[32];
+  double v2 = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const double d = eloc[i] - meanE;
+    if (dE) dE[i] = d;
+    if (wE) wE[i] = d * d;
+    if (wLp) wLp[i] = logp[i] * logp[i];
+    v2 += d * d;
+  }
+  const double r = block_reduce_sum(v2, shs);
+  if (threadIdx.x == 0 && var_sum) var_sum[0] += r;
 }
 
 // upper triangle scaled and mirrored into the lower one, 32x32 tiles through shared memory
@@ -148,28 +168,55 @@ __global__ void diag_shift_kernel(const double* __restrict__ S, double* __restri
 
 }  // namespace vmc
 
+extern "C" __attribute__((visibility("default"))) int vmcpde_moments_workspace_bytes(int64_t n, int64_t ldo, size_t* bytes) {
+  using namespace vmc;
+  VMC_REQUIRE(bytes && n >= 0 && ldo >= 0, "vmcpde_moments_workspace_bytes: bad arguments");
+  const long long row_blocks = (n + kRowsPerCta - 1) / kRowsPerCta;
+  *bytes = (size_t)(row_blocks > 0 ? row_blocks : 1) * (size_t)ldo * 8;
+  return 0;
+}
+
 extern "C" __attribute__((visibility("default"))) int vmcpde_moments1(const double* eloc, const double* logp, const double* O, int64_t n, int64_t ldo,
-                               double* sums, vmcpde_stream stream) {
+                               double* sums, void* workspace, size_t workspace_bytes, vmcpde_stream stream) {
   using namespace vmc;
   VMC_REQUIRE(sums, "vmcpde_moments1: null sums");
   if (n <= 0) return 0;
-  const int col_ctas = O ? (int)((ldo + kColsPerCta - 1) / kColsPerCta) : 0;
-  moments1_kernel<<<col_ctas + 1, kColThreads, 0, (cudaStream_t)stream>>>(eloc, logp, O, n, ldo, sums, col_ctas);
-  VMC_LAUNCH_CHECK("moments1_kernel");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (O) {
+    VMC_REQUIRE(ldo % 2 == 0 && ((uintptr_t)O & 15) == 0, "vmcpde_moments1: O must be 16-byte aligned with an even ldo");
+    size_t need = 0;
+    vmcpde_moments_workspace_bytes(n, ldo, &need);
+    VMC_REQUIRE(workspace && workspace_bytes >= need, "vmcpde_moments1: workspace too small");
+    const int row_blocks = (int)((n + kRowsPerCta - 1) / kRowsPerCta);
+    const dim3 grid((unsigned)((ldo + kTileCols - 1) / kTileCols), (unsigned)row_blocks);
+    rowblock_kernel<false><<<grid, kRT, 0, s>>>(const_cast<double*>(O), n, ldo, nullptr, nullptr, 0.0, (double*)workspace);
+    colsum_partials_kernel<<<(unsigned)((ldo + 255) / 256), 256, 0, s>>>((const double*)workspace, row_blocks, ldo, sums + 4);
+  }
+  scalar_moments_kernel<<<1, 1024, 0, s>>>(eloc, logp, n, sums);
+  VMC_LAUNCH_CHECK("moments1");
   return 0;
 }
 
 extern "C" __attribute__((visibility("default"))) int vmcpde_center_force(double* O, int64_t n, int64_t ldo, const double* meanO, const double* eloc,
                                    const double* logp, double meanE, double* dE, double* wE, double* wLp,
-                                   double* Fsum, double* var_sum, vmcpde_stream stream) {
+                                   double* Fsum, double* var_sum, void* workspace, size_t workspace_bytes,
+                                   vmcpde_stream stream) {
   using namespace vmc;
   VMC_REQUIRE(O && meanO && eloc && Fsum, "vmcpde_center_force: null pointer");
   VMC_REQUIRE(!wLp || logp, "vmcpde_center_force: wLp requires logp");
   if (n <= 0) return 0;
-  const int col_ctas = (int)((ldo + kColsPerCta - 1) / kColsPerCta);
-  center_force_kernel<<<col_ctas + 1, kColThreads, 0, (cudaStream_t)stream>>>(O, n, ldo, meanO, eloc, logp, meanE, dE, wE,
-                                                                              wLp, Fsum, var_sum, col_ctas);
-  VMC_LAUNCH_CHECK("center_force_kernel");
+  VMC_REQUIRE(ldo % 2 == 0 && ((uintptr_t)O & 15) == 0 && ((uintptr_t)meanO & 15) == 0,
+              "vmcpde_center_force: O / meanO must be 16-byte aligned with an even ldo");
+  size_t need = 0;
+  vmcpde_moments_workspace_bytes(n, ldo, &need);
+  VMC_REQUIRE(workspace && workspace_bytes >= need, "vmcpde_center_force: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int row_blocks = (int)((n + kRowsPerCta - 1) / kRowsPerCta);
+  const dim3 grid((unsigned)((ldo + kTileCols - 1) / kTileCols), (unsigned)row_blocks);
+  rowblock_kernel<true><<<grid, kRT, 0, s>>>(O, n, ldo, meanO, eloc, meanE, (double*)workspace);
+  colsum_partials_kernel<<<(unsigned)((ldo + 255) / 256), 256, 0, s>>>((const double*)workspace, row_blocks, ldo, Fsum);
+  sample_weights_kernel<<<1, 1024, 0, s>>>(eloc, logp, n, meanE, dE, wE, wLp, var_sum);
+  VMC_LAUNCH_CHECK("center_force");
   return 0;
 }
 

@@ -94,13 +94,23 @@ __global__ void __launch_bounds__(256) transpose_kernel(const double* __restrict
   for (int r = ty; r < 32; r += 8) B[(size_t)(c0 + r) * ld + r0 + tx] = tile[tx][r];
 }
 
+// rows [r0, r0 + 32 * gridDim.y) of A become the same columns of B (B[c][r] = A[r][c], c < ld)
+__global__ void __launch_bounds__(256) transpose_rows_kernel(const double* __restrict__ A, double* __restrict__ B, int ld, int r0) {
+  __shared__ double tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int rr = r0 + blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int r = ty; r < 32; r += 8) tile[r][tx] = A[(size_t)(rr + r) * ld + c0 + tx];
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) B[(size_t)(c0 + r) * ld + rr + tx] = tile[tx][r];
+}
+
 // tdvp.py:70-71,82-89: rhoVar, snr, invEv, regulariser -> coefficient in the eigenbasis
 __global__ void solve_coef_kernel(const double* __restrict__ ev, const double* __restrict__ VtF,
                                   const double* __restrict__ q, int n, double n_glob, double svdTol, double snrTol,
                                   int useSNR, double* __restrict__ rhoVar, double* __restrict__ snr,
-                                  double* __restrict__ invEv, double* __restrict__ coef) {
+                                  double* __restrict__ invEv, double* __restrict__ coef, int k0, int k1) {
   const double evmax = ev[n - 1];
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+  for (int k = k0 + blockIdx.x * blockDim.x + threadIdx.x; k < k1; k += gridDim.x * blockDim.x) {
     const double f = VtF[k];
     double sn = 0.0;
     if (q) {
@@ -308,6 +318,49 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_solve_tail_workspac
   return 0;
 }
 
+// The eigenvector-local part of TDVP.solve / transform_to_eigenbasis (tdvp.py:66-92) for the eigenvectors
+// [row0, row0 + nrows) (rows of VT; multiples of 128 when CEO is given): VtF, rhoVar, snr, invEv on that range and
+// update_partial[n] = sum_{k in range} V[:,k] invEv_k reg_k VtF_k.  A multi-GPU solve gives every rank a slice and sums
+// update_partial (and the range vectors, zero elsewhere) with one all-reduce; one rank with the full range gets
+// the reference's result.  Entries of the output vectors outside the range are not written.
+extern "C" __attribute__((visibility("default"))) int vmcpde_solve_tail_range(
+    const double* ev, const double* VT, int32_t n, int32_t ld, const double* F, const double* CEO, double n_glob,
+    double svdTol, double snrTol, int32_t useSNR, int32_t row0, int32_t nrows, double* VtF, double* rhoVar, double* snr,
+    double* invEv, double* update_partial, void* workspace, size_t workspace_bytes, vmcpde_stream stream) {
+  VMC_REQUIRE(ev && VT && F && VtF && invEv && update_partial && workspace, "vmcpde_solve_tail_range: null pointer");
+  VMC_REQUIRE(!useSNR || CEO, "vmcpde_solve_tail_range: useSNR needs the SNR covariance");
+  VMC_REQUIRE(!CEO || (rhoVar && snr), "vmcpde_solve_tail_range: rhoVar/snr outputs required with CEO");
+  VMC_REQUIRE(!CEO || (ld % 128 == 0 && row0 % 128 == 0 && nrows % 128 == 0), "vmcpde_solve_tail_range: ld, row0, nrows must be multiples of 128");
+  VMC_REQUIRE(row0 >= 0 && nrows > 0 && row0 + nrows <= ld, "vmcpde_solve_tail_range: bad range");
+  size_t need = 0;
+  vmcpde_solve_tail_workspace_bytes(n, ld, &need);
+  VMC_REQUIRE(workspace_bytes >= need, "vmcpde_solve_tail_range: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  uint8_t* wp = (uint8_t*)workspace;
+  double* V = (double*)wp; wp += al((size_t)ld * ld * 8);
+  double* W = (double*)wp; wp += al((size_t)ld * ld * 8);
+  double* q = (double*)wp; wp += al((size_t)ld * 8);
+  double* coef = (double*)wp; wp += al((size_t)ld * 8);
+  const int sms = num_sms();
+  const int k0 = row0, k1 = min(n, row0 + nrows), nk = k1 - k0;  // real eigenvectors of the range
+  if (nk <= 0) {
+    VMC_CUDA_CHECK(cudaMemsetAsync(update_partial, 0, (size_t)n * 8, s));
+    return 0;
+  }
+  const int rb = max(1, min(sms * 4, (nk + 7) / 8));
+  gemv_rows_kernel<<<rb, 256, 0, s>>>(VT + (size_t)k0 * ld, ld, nk, n, F, VtF + k0);
+  if (CEO) {
+    transpose_rows_kernel<<<dim3(ld / 32, nrows / 32), 256, 0, s>>>(VT, V, ld, row0);
+    if (int rc = vmcpde_gemm_tn(CEO, ld, V + row0, ld, W + row0, ld, ld, nrows, ld, 1.0, 0.0, stream)) return rc;
+    coldot_kernel<<<(nk + 31) / 32, 256, 0, s>>>(V + k0, W + k0, ld, n, nk, q + k0);
+  }
+  solve_coef_kernel<<<max(1, min(sms, (nk + 255) / 256)), 256, 0, s>>>(ev, VtF, CEO ? q : nullptr, n, n_glob, svdTol, snrTol,
+                                                                     useSNR, rhoVar, snr, invEv, coef, k0, k1);
+  gemv_cols_kernel<<<(n + 31) / 32, 256, 0, s>>>(VT + (size_t)k0 * ld, ld, nk, n, coef + k0, update_partial);
+  VMC_LAUNCH_CHECK("solve_tail_range");
+  return 0;
+}
+
 // Everything after eigh in TDVP.solve / transform_to_eigenbasis (tdvp.py:66-94).
 // ev[n] ascending, VT[n x ld] rows = eigenvectors (pad region zero), F[n], S (shifted) and S0 [n x ld] full symmetric,
 // CEO [ld x ld] = (1/N) sum dE^2 dO dO^T (padded, zero pad) or NULL to skip the SNR.
@@ -317,32 +370,17 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_solve_tail(
     const double* CEO, double n_glob, double svdTol, double snrTol, int32_t useSNR, double meanE2, double* VtF,
     double* rhoVar, double* snr, double* invEv, double* update, double* scalars, void* workspace,
     size_t workspace_bytes, vmcpde_stream stream) {
-  VMC_REQUIRE(ev && VT && F && S && S0 && VtF && invEv && update && scalars && workspace, "vmcpde_solve_tail: null pointer");
-  VMC_REQUIRE(!useSNR || CEO, "vmcpde_solve_tail: useSNR needs the SNR covariance");
-  VMC_REQUIRE(!CEO || (rhoVar && snr), "vmcpde_solve_tail: rhoVar/snr outputs required with CEO");
+  VMC_REQUIRE(S && S0 && scalars && update && workspace, "vmcpde_solve_tail: null pointer");
   VMC_REQUIRE(!CEO || ld % 128 == 0, "vmcpde_solve_tail: ld must be a multiple of 128");
-  size_t need = 0;
-  vmcpde_solve_tail_workspace_bytes(n, ld, &need);
-  VMC_REQUIRE(workspace_bytes >= need, "vmcpde_solve_tail: workspace too small");
-  cudaStream_t s = (cudaStream_t)stream;
-  uint8_t* wp = (uint8_t*)workspace;
-  double* V = (double*)wp; wp += al((size_t)ld * ld * 8);
-  double* W = (double*)wp; wp += al((size_t)ld * ld * 8);
-  double* q = (double*)wp; wp += al((size_t)ld * 8);
-  double* coef = (double*)wp; wp += al((size_t)ld * 8);
+  const int nrows = CEO ? ld : n;
+  if (int rc = vmcpde_solve_tail_range(ev, VT, n, ld, F, CEO, n_glob, svdTol, snrTol, useSNR, 0, nrows, VtF, rhoVar, snr, invEv,
+                                       update, workspace, workspace_bytes, stream))
+    return rc;
+  uint8_t* wp = (uint8_t*)workspace + 2 * al((size_t)ld * ld * 8) + 2 * al((size_t)ld * 8);
   double* Su = (double*)wp; wp += al((size_t)ld * 8);
-  double* S0u = (double*)wp; wp += al((size_t)ld * 8);
-  const int sms = num_sms();
-  const int rb = max(1, min(sms * 4, (n + 7) / 8));
-  gemv_rows_kernel<<<rb, 256, 0, s>>>(VT, ld, n, n, F, VtF);
-  if (CEO) {
-    transpose_kernel<<<dim3(ld / 32, ld / 32), 256, 0, s>>>(VT, V, ld);
-    if (int rc = vmcpde_gemm_tn(CEO, ld, V, ld, W, ld, ld, ld, ld, 1.0, 0.0, stream)) return rc;
-    coldot_kernel<<<(n + 31) / 32, 256, 0, s>>>(V, W, ld, n, n, q);
-  }
-  solve_coef_kernel<<<max(1, min(sms, (n + 255) / 256)), 256, 0, s>>>(ev, VtF, CEO ? q : nullptr, n, n_glob, svdTol, snrTol,
-                                                                    useSNR, rhoVar, snr, invEv, coef);
-  gemv_cols_kernel<<<(n + 31) / 32, 256, 0, s>>>(VT, ld, n, n, coef, update);
+  double* S0u = (double*)wp;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int rb = max(1, min(num_sms() * 4, (n + 7) / 8));
   gemv_rows_kernel<<<rb, 256, 0, s>>>(S, ld, n, n, update, Su);
   gemv_rows_kernel<<<rb, 256, 0, s>>>(S0, ld, n, n, update, S0u);
   solve_scalars_kernel<<<1, 1024, 0, s>>>(Su, S0u, F, update, n, meanE2, scalars);

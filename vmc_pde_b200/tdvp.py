@@ -22,6 +22,14 @@ import torch
 from . import _kernels, mpi_wrapper as mpi, global_defs
 
 
+def solve_shard_range(Pp, world, rank):
+    """Eigenvector slice [row0, row0 + nrows) of rank `rank` in a sharded solve: the Pp / 128 blocks of 128 eigenvectors
+    are dealt contiguously; ranks beyond the block count get an empty slice."""
+    nblk = Pp // 128
+    b0, b1 = rank * nblk // world, (rank + 1) * nblk // world
+    return 128 * b0, 128 * (b1 - b0)
+
+
 @dataclass
 class TDVP:
     useSNR: bool = False
@@ -33,6 +41,7 @@ class TDVP:
     solver: str = "eigh"               # "eigh" | "cholesky" (needs diagonalShift > 0; no ev / V / snr)
     computeSExp: bool = True           # SExp is only read by AdaptiveHeun (stepper.py:71)
     computeSNR: bool = True            # snr is logged by main.py:187 and gates the solve when useSNR
+    shardSolve: bool = True            # several ranks: shard the post-tridiagonal O(P^3) stages over eigenvectors
     chunkSamples: int = 0              # samples per chunk (0 = choose from free memory)
     memoryFraction: float = 0.45       # share of free device memory the O buffer may take
 
@@ -40,10 +49,26 @@ class TDVP:
         if self.solver not in ("eigh", "cholesky"):
             raise ValueError("solver must be 'eigh' or 'cholesky'")
         self._bufP = None
-        self.S = self.S0 = self.F0 = self.SExp = self.ev = self.V = self.VtF = None
+        self._P = None
+        self._vt_range = None
+        self.S = self.S0 = self.F0 = self.SExp = self.ev = self.VtF = None
         self.rhoVar = self.snr = self.invEv = None
         self.solverResidual = self.tdvp_error = None
         self.ElocMean = self.ElocMeanAbs = self.ElocVar = None
+
+    @property
+    def V(self):
+        """Eigenvectors as columns (tdvp.py:59-64).  With a sharded solve every rank holds a slice of eigenvectors;
+        the full matrix is assembled (one all-reduce of the zero-padded P x P buffer) on first access only."""
+        if self._P is None:
+            return None
+        if self._vt_range is not None:
+            row0, nrows = self._vt_range
+            self._VT[:row0].zero_()
+            self._VT[row0 + nrows:].zero_()
+            mpi.allreduce_(self._VT)
+            self._vt_range = None
+        return self._VT[:self._P, :self._P].T
 
     # ------------------------------------------------------------------------------------------------
     def _buffers(self, P, Pp):
@@ -112,11 +137,30 @@ class TDVP:
         self._Swork.copy_(S)
         if self.solver == "eigh":
             ws = _kernels.workspace(_kernels.eigh_workspace_bytes(P, Pp))
-            _kernels.eigh(self._Swork, P, Pp, ev, self._VT, ws)
-            _kernels.solve_tail(ev, self._VT, P, Pp, F, S, S0, CEO if use_ceo else None, float(N), self.svdTol, self.snrTol,
-                                self.useSNR, meanE2, VtF, rhoVar if use_ceo else None, snr if use_ceo else None, invEv, update,
-                                self._scal, ws)
-            self.ev, self.V, self.VtF, self.invEv = ev[:P], self._VT[:P, :P].T, VtF[:P], invEv[:P]
+            R, rank = mpi.comm.Get_size(), mpi.comm.Get_rank()
+            nblk = Pp // 128
+            self._vt_range = None
+            if R > 1 and nblk >= R and self.shardSolve:
+                # Tridiagonalisation and divide & conquer are replicated (every rank holds the all-reduced S); the O(P^3)
+                # stages after them -- back-transformation, V^T C V for the SNR, the update -- are sharded over the
+                # eigenvector index in blocks of 128 and joined by one all-reduce of 5 P doubles.
+                row0, nrows = solve_shard_range(Pp, R, rank)
+                vec = self._vecs[1:6]
+                vec.zero_()
+                _kernels.eigh_cols(self._Swork, P, Pp, ev, self._VT, row0, nrows, ws)
+                _kernels.solve_tail_range(ev, self._VT, P, Pp, F, CEO if use_ceo else None, float(N), self.svdTol, self.snrTol,
+                                          self.useSNR, row0, nrows, VtF, rhoVar if use_ceo else None, snr if use_ceo else None,
+                                          invEv, update, ws)
+                mpi.allreduce_(vec)
+                _kernels.solve_scalars(S, S0, P, Pp, F, update, meanE2, self._scal, self._vecs[6:8].reshape(-1))
+                self._vt_range = (row0, nrows)
+            else:
+                _kernels.eigh(self._Swork, P, Pp, ev, self._VT, ws)
+                _kernels.solve_tail(ev, self._VT, P, Pp, F, S, S0, CEO if use_ceo else None, float(N), self.svdTol, self.snrTol,
+                                    self.useSNR, meanE2, VtF, rhoVar if use_ceo else None, snr if use_ceo else None, invEv, update,
+                                    self._scal, ws)
+            self._P = P
+            self.ev, self.VtF, self.invEv = ev[:P], VtF[:P], invEv[:P]
             self.rhoVar, self.snr = (rhoVar[:P], snr[:P]) if use_ceo else (None, None)
         else:
             if not self.diagonalShift > 1e-10:
@@ -126,7 +170,8 @@ class TDVP:
             _kernels.solve_scalars(S, S0, P, Pp, F, update, meanE2, self._scal, self._vecs[6:8].reshape(-1))
             if int(self._info.item()) != 0:
                 raise RuntimeError(f"Cholesky failed: non-positive pivot at index {int(self._info.item()) - 1}")
-            self.ev = self.V = self.VtF = self.invEv = self.rhoVar = self.snr = None
+            self._P = None
+            self.ev = self.VtF = self.invEv = self.rhoVar = self.snr = None
         self.solverResidual, self.tdvp_error = self._scal[0].clone(), self._scal[1].clone()
         return update[:P].clone()
 
