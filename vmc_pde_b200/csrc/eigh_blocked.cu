@@ -49,17 +49,43 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// all CTAs of the (cooperative) grid; `target` counts the arrivals expected so far.  The arrival is a release
-// reduction (no return value to wait for: polling starts at once), the poll an acquire load; bar.sync on both
-// sides extends the ordering to the whole CTA.
-__device__ __forceinline__ void grid_sync(unsigned* bar, unsigned& target) {
+// Barrier over all CTAs of the (cooperative) grid.  148 same-address atomics serialise at L2 (~27 cycles each, ~4000
+// cycles per barrier on B200) and 148 x 148 flag polls hot-spot a handful of lines (measured: worse), so arrivals are
+// spread over 16 counters on separate 128-byte lines and one warp per CTA polls their sum.  Arrival is a release
+// reduction (covers the CTA's earlier writes through the preceding bar.sync); the poll is relaxed, followed by one
+// acquire fence; the closing bar.sync extends the ordering to the whole CTA.  Counters only grow (epoch * grid).
+constexpr int kBarCounters = 16, kBarStride = 32;
+__device__ __forceinline__ void grid_sync(unsigned* ctr, unsigned& epoch) {
   __syncthreads();
-  if (threadIdx.x == 0) {
-    target += gridDim.x;
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
-    while (ld_acquire_u32(bar) < target) {}
+  ++epoch;
+  if (threadIdx.x < 32) {
+    if (threadIdx.x == 0)
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr + (blockIdx.x % kBarCounters) * kBarStride) : "memory");
+    const unsigned target = epoch * gridDim.x;
+    unsigned sum;
+    do {
+      unsigned v = 0;
+      if (threadIdx.x < kBarCounters)
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr + threadIdx.x * kBarStride) : "memory");
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      sum = __shfl_sync(0xffffffffu, v, 0);
+    } while (sum < target);
+    __threadfence();
   }
   __syncthreads();
+}
+
+// 16-byte value + sequence-number message (the flag travels with the data, as in NCCL's LL protocol)
+__device__ __forceinline__ void ll_store(double* slot, double v, unsigned long long seq) {
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(__double_as_longlong(v)), "l"(seq) : "memory");
+}
+__device__ __forceinline__ double ll_load(const double* slot, unsigned long long seq) {
+  unsigned long long v, sq;
+  do {
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v), "=l"(sq) : "l"(slot) : "memory");
+  } while (sq != seq);
+  return __longlong_as_double((long long)v);
 }
 
 __device__ __forceinline__ int gcd16(int a) {  // gcd(a, 16) for a >= 1
@@ -83,10 +109,23 @@ struct PanelArgs {
   double* Y;               // [2 nb][ld]: rows k: w_k, rows nb + k: v_k, zero for index < j1
   double* Z;               // [grid][ld] column-part partial products of the symmetric mat-vec (NULL: full rows only)
   int sym_min_m;           // columns with a trailing size >= this read only the lower triangle
-  unsigned* bar;
+  long long* prof;         // optional per-phase cycle counters of CTA 0 (VMCPDE_PANEL_PROFILE)
+  unsigned* bar;           // barrier counters
+  unsigned epoch0;         // barrier epochs completed before this launch
+  double* totals;          // [2 nb + 1][2] reduced partials as (value, sequence) messages
 };
 
+#define VMC_PROF(k)                                                          \
+  do {                                                                       \
+    if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) {                     \
+      const long long t_ = clock64();                                        \
+      a.prof[k] += t_ - tprof;                                               \
+      tprof = t_;                                                            \
+    }                                                                        \
+  } while (0)
+
 __global__ void __launch_bounds__(kPT, 1) tridiag_panel_kernel(const __grid_constant__ PanelArgs a) {
+  long long tprof = clock64();
   extern __shared__ __align__(16) double sm[];
   const int n = a.n, ld = a.ld, nb = a.nb, G = gridDim.x, b = blockIdx.x, tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -114,7 +153,7 @@ __global__ void __launch_bounds__(kPT, 1) tridiag_panel_kernel(const __grid_cons
 
   for (int idx = tid; idx < 2 * S * ldo; idx += kPT) own_v[idx] = 0.0;
   for (int idx = tid; idx < nv; idx += kPT) vs[idx] = 0.0;
-  unsigned target = 0;
+  unsigned target = a.epoch0;
   {  // prologue: pivot row of the first column (the trailing matrix is up to date)
     double s = 0.0;
     if (tid < S) {
@@ -140,9 +179,10 @@ __global__ void __launch_bounds__(kPT, 1) tridiag_panel_kernel(const __grid_cons
       rowW[tid] = __ldcg(a.wrows + (size_t)tid * ldo + i + 1);
     }
     // next pivot row of the (panel-start) trailing matrix on the rows of this CTA: issued now, used in phase B
+    double anext_reg = 0.0;   // stays in flight during phase A; parked in shared memory before the first barrier
     if (tid < S) {
       const int r = row_of_slot(tid);
-      anext[tid] = (i + 1 < a.nbp && r > j && r < n) ? __ldg(a.A + (size_t)(j + 1) * ld + r) : 0.0;
+      if (i + 1 < a.nbp && r > j && r < n) anext_reg = __ldg(a.A + (size_t)(j + 1) * ld + r);
     }
     if (have) {
       // ---------------- phase A: reflector, y = A22 v on the rows of this CTA, partial dots ----------------
@@ -150,6 +190,7 @@ __global__ void __launch_bounds__(kPT, 1) tridiag_panel_kernel(const __grid_cons
       const double sg = tid < G ? __ldcg(a.psig + tid) : 0.0;
       for (int c = tid; c < n; c += kPT) vs[c] = c > j ? __ldcg(a.acol + c) : 0.0;
       const double sigma = bsum_(sg, red);
+      VMC_PROF(0);
       const double alpha = vs[j + 1];
       double beta = alpha, scale = 0.0;
       if (sigma != 0.0) {
@@ -180,6 +221,7 @@ __global__ void __launch_bounds__(kPT, 1) tridiag_panel_kernel(const __grid_cons
         own_v[tid * ldo + i] = val;
         vown[tid] = val;
       }
+      VMC_PROF(1);
       // y = A22 v: 4-row chunks x column segments over the warps
       const int qfirst = (j + 1) / kRC;
       const int lq0 = qfirst > b ? (qfirst - b + G - 1) / G : 0;
@@ -308,6 +350,7 @@ __global__ void __launch_bounds__(kPT, 1) tridiag_panel_kernel(const __grid_cons
       }
       }
       __syncthreads();
+      VMC_PROF(2);
       double yvp = 0.0;   // this thread's share of y.v
       if (tid < S) {
         const int ch = (tid >> 2) - lq0, r = row_of_slot(tid);
@@ -335,10 +378,13 @@ __global__ void __launch_bounds__(kPT, 1) tridiag_panel_kernel(const __grid_cons
         for (int q = 0; q < S; ++q) s = fma(arr[q * ldo + k], vown[q], s);
         a.part[(size_t)((tid < i ? 0 : nb) + k) * G + b] = s;
       }
+      if (tid < S) anext[tid] = anext_reg;
       yvp = bsum_(yvp, red);
       if (tid == 0) a.part[(size_t)(2 * nb) * G + b] = yvp;
       if (tid < S && row_of_slot(tid) == j + 1) a.part[(size_t)(2 * nb + 1) * G] = ys[tid];
+      VMC_PROF(3);
       grid_sync(a.bar, target);
+      VMC_PROF(4);
       // ---------------- phase B: reduce the partials ----------------
       if (sym) {
         // y on the rows of this CTA += column parts of all CTAs (8 lanes per row, fixed order)
@@ -363,34 +409,25 @@ __global__ void __launch_bounds__(kPT, 1) tridiag_panel_kernel(const __grid_cons
       } else if (tid == 0) {
         red[42] = 0.0;
       }
-      const int nred = 2 * i + 1;
-      {  // all loads of a warp are issued before the first reduction (one L2 round trip instead of nred / 16)
-        constexpr int kU = 9, kQ = 5;  // 2 * 64 + 1 values over 16 warps; up to 160 CTAs
-        double acc[kU];
-#pragma unroll
-        for (int u = 0; u < kU; ++u) {
-          const int t = warp + u * kPW;
-          const int kk = t < i ? t : (t < 2 * i ? nb + (t - i) : 2 * nb);
-          double sacc = 0.0;
-          if (t < nred) {
-#pragma unroll
-            for (int q = 0; q < kQ; ++q) {
-              const int bb = lane + 32 * q;
-              if (bb < G) sacc += __ldcg(a.part + (size_t)kk * G + bb);
-            }
-            for (int bb = lane + 32 * kQ; bb < G; bb += 32) sacc += __ldcg(a.part + (size_t)kk * G + bb);
+      {  // Value t of the 2 i + 1 reduced partials is summed by CTA t (warp 0, coalesced, fixed order) and published as
+         // a (value, sequence) message; every CTA then collects all of them.  Two L2 round trips, no all-to-all reads.
+        const int nred = 2 * i + 1;
+        const unsigned long long seq = (unsigned long long)j + 1;
+        for (int t = b; t < nred; t += G) {
+          if (warp == 0) {
+            const int kk = t < i ? t : (t < 2 * i ? nb + (t - i) : 2 * nb);
+            const double* src = a.part + (size_t)kk * G;
+            double sacc = 0.0;
+            for (int q = lane; q < G; q += 32) sacc += __ldcg(src + q);
+            sacc = wsum_(sacc);
+            if (lane == 0) ll_store(a.totals + 2 * t, sacc, seq);
           }
-          acc[u] = sacc;
         }
-#pragma unroll
-        for (int u = 0; u < kU; ++u) {
-          const int t = warp + u * kPW;
-          const double sred = wsum_(acc[u]);
-          if (lane == 0 && t < nred) {
-            if (t < i) PV[t] = sred;
-            else if (t < 2 * i) PWs[t - i] = sred;
-            else red[40] = sred;
-          }
+        for (int t = tid; t < nred; t += kPT) {
+          const double v = ll_load(a.totals + 2 * t, seq);
+          if (t < i) PV[t] = v;
+          else if (t < 2 * i) PWs[t - i] = v;
+          else red[40] = v;
         }
       }
       if (tid == kPT - 1) red[41] = __ldcg(a.part + (size_t)(2 * nb + 1) * G);
@@ -406,19 +443,28 @@ __global__ void __launch_bounds__(kPT, 1) tridiag_panel_kernel(const __grid_cons
         a.X[(size_t)(nb + i) * ld + c] = 0.0; a.Y[(size_t)i * ld + c] = 0.0;
       }
       if (b == 0 && tid <= nb) { a.vrows[(size_t)i * ldo + tid] = 0.0; a.wrows[(size_t)i * ldo + tid] = 0.0; }
-      if (tid < S) { vown[tid] = 0.0; ys[tid] = 0.0; }
+      if (tid < S) { vown[tid] = 0.0; ys[tid] = 0.0; anext[tid] = anext_reg; }
       if (tid == 0) { red[40] = 0.0; red[41] = 0.0; red[42] = 0.0; }
     }
     __syncthreads();
-    // scalars of the column (every thread, from shared memory)
-    double pvdot = 0.0, c1 = 0.0;
-    for (int k = 0; k < i; ++k) {
-      pvdot = fma(PV[k], PWs[k], pvdot);
-      c1 = fma(rowV[k], PWs[k], c1);
-      c1 = fma(rowW[k], PV[k], c1);
+    VMC_PROF(5);
+    // scalars of the column: one warp reduces, everybody reads them back (16 warps repeating the loop would
+    // queue on the FP64 pipe)
+    if (warp == 0) {
+      double pd = 0.0, cd = 0.0;
+      for (int k = lane; k < i; k += 32) {
+        pd = fma(PV[k], PWs[k], pd);
+        cd = fma(rowV[k], PWs[k], cd);
+        cd = fma(rowW[k], PV[k], cd);
+      }
+      pd = wsum_(pd); cd = wsum_(cd);
+      if (lane == 0) { red[43] = pd; red[44] = cd; }
     }
+    __syncthreads();
+    const double pvdot = red[43], c1 = red[44];
     const double pv = have ? tau_j * (red[40] - 2.0 * pvdot) : 0.0;   // p.v with p = tau * (corrected y)
     const double w1 = have ? tau_j * (red[41] + red[42] - c1) - 0.5 * tau_j * pv : 0.0;  // w at the next pivot row
+    VMC_PROF(6);
     // w on the rows of this CTA and the next pivot row, 8 lanes per slot
     double sg2 = 0.0;
     for (int base = 0; base < S; base += kPT / 8) {
@@ -457,7 +503,9 @@ __global__ void __launch_bounds__(kPT, 1) tridiag_panel_kernel(const __grid_cons
     }
     sg2 = bsum_(sg2, red);
     if (tid == 0) a.psig[b] = sg2;
+    VMC_PROF(7);
     grid_sync(a.bar, target);
+    VMC_PROF(8);
   }
 }
 
@@ -630,7 +678,8 @@ size_t blocked_tridiag_scratch_bytes(int n, int ld) {
   if (!plan_panel(n, &p)) return 0;
   const int nb = p.nb, G = p.grid;
   return al256((size_t)ld * 8) + al256((size_t)(2 * nb + 2) * G * 8) + al256((size_t)G * 8) +
-         2 * al256((size_t)nb * (nb + 1) * 8) + 2 * al256((size_t)2 * nb * ld * 8) + al256(((size_t)n / nb + 2) * 4) +
+         2 * al256((size_t)nb * (nb + 1) * 8) + 2 * al256((size_t)2 * nb * ld * 8) + al256((size_t)kBarCounters * kBarStride * 4) +
+         al256((size_t)(2 * nb + 1) * 16) +
          (p.sym ? al256((size_t)G * ld * 8) : 0);
 }
 
@@ -662,17 +711,28 @@ int tridiag_blocked(double* A, int n, int ld, double* d, double* e, double* tau,
   a.X = (double*)take((size_t)2 * nb * ld * 8);
   a.Y = (double*)take((size_t)2 * nb * ld * 8);
   const int panels = (n + nb - 1) / nb;
-  unsigned* bars = (unsigned*)take(((size_t)panels + 2) * 4);
+  unsigned* bars = (unsigned*)take((size_t)kBarCounters * kBarStride * 4);
+  a.totals = (double*)take((size_t)(2 * nb + 1) * 16);
+  long long* prof = nullptr;
+  if (getenv("VMCPDE_PANEL_PROFILE")) {
+    VMC_CUDA_CHECK(cudaMalloc(&prof, 16 * sizeof(long long)));
+    VMC_CUDA_CHECK(cudaMemsetAsync(prof, 0, 16 * sizeof(long long), s));
+  }
+  a.prof = prof;
   VMC_CUDA_CHECK(cudaMemsetAsync(a.acol, 0, (size_t)(wp - (uint8_t*)a.acol), s));
   a.Z = p.sym ? (double*)take((size_t)G * ld * 8) : nullptr;
   a.sym_min_m = 1536;
   if (const char* e_ = getenv("VMCPDE_EIGH_SYM_MIN_M")) a.sym_min_m = atoi(e_);
   VMC_CUDA_CHECK(cudaFuncSetAttribute(tridiag_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+  unsigned epoch = 0;
   for (int pi = 0; pi < panels; ++pi) {
     a.j0 = pi * nb;
     a.nbp = min(nb, n - a.j0);
     a.j1 = a.j0 + nb;
-    a.bar = bars + pi;
+    a.bar = bars;
+    a.epoch0 = epoch;
+    epoch += 1;                          // barriers of this launch: prologue, then 2 per reflector column (1 for the last two)
+    for (int i = 0; i < a.nbp; ++i) epoch += (n - (a.j0 + i) - 1 >= 2) ? 2 : 1;
     void* kargs[] = {(void*)&a};
     VMC_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)tridiag_panel_kernel, dim3(G), dim3(kPT), kargs, p.smem, s));
     if (a.j1 < n) {
@@ -683,6 +743,18 @@ int tridiag_blocked(double* A, int n, int ld, double* d, double* e, double* tau,
     }
   }
   VMC_LAUNCH_CHECK("tridiag_blocked");
+  if (prof) {  // debugging aid: synchronises
+    long long h[16];
+    cudaStreamSynchronize(s);
+    cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(prof);
+    const char* names[9] = {"A: loads + norm", "A: build v, writes", "A: mat-vec", "A: y, partial dots", "barrier 1",
+                            "B: gather + reduce", "B: scalars", "B: w, next pivot row", "barrier 2"};
+    long long tot = 0;
+    for (int k = 0; k < 9; ++k) tot += h[k];
+    fprintf(stderr, "[tridiag_panel_kernel n=%d] CTA 0 cycles per column by phase (total %.0f):\n", n, (double)tot / n);
+    for (int k = 0; k < 9; ++k) fprintf(stderr, "   %-24s %9.0f  %5.1f%%\n", names[k], (double)h[k] / n, 100.0 * h[k] / tot);
+  }
   return 0;
 }
 
