@@ -206,6 +206,9 @@ def test_driver_loop_like_main_py():
     assert abs(float(torch.diagonal(info["covar"]).mean()) - (1 + 2 * (t - dt))) < 0.08
     x0, _ = vs.net.apply(vs.params, np.zeros(2), evaluate=False, inv=True)                     # main.py:202
     assert x0.shape == (2,)
+    from vmc_pde_b200 import grid                                                              # main.py:100-104,195
+    g = grid.Grid(np.ones(2) * 12.0, 200, sym=True)
+    assert abs(vs.integrate(g) - 1.0) < 2e-3       # the flow density stays normalised along the evolution
 
 
 def test_full_size_properties_c3():

@@ -59,6 +59,23 @@ def test_distribute_sampling_arithmetic():
     assert mpi_wrapper.rank == 0 and mpi_wrapper.commSize == 1
 
 
+def test_grid_geometry_matches_reference_layout():
+    """grid.py:7-29: widths, cell area, origin list in meshgrid('xy') order, symmetric and one-sided variants."""
+    from vmc_pde_b200 import grid
+    g = grid.Grid(np.array([2.0, 3.0]), 4, sym=True)
+    assert g.dim == 2 and np.allclose(g.widths, [1.0, 1.5]) and abs(g.bin_area - 1.5) < 1e-15
+    assert g.range == [[-2.0, 2.0], [-3.0, 3.0]] and g.coords.shape == (16, 2)
+    xs, ys = np.arange(-2, 2, 1.0), np.arange(-3, 3, 1.5)
+    ref = np.moveaxis(np.array(np.meshgrid(xs, ys)), 0, -1).reshape(16, 2)     # the reference's construction
+    assert np.array_equal(g.coords, ref)
+    g1 = grid.Grid(np.array([2.0, 2.0]), 5, sym=False)
+    assert np.allclose(g1.widths, 0.4) and g1.range == [[0.0, 2.0], [0.0, 2.0]] and g1.coords.min() == 0.0
+    # a unit Gaussian integrates to ~1 on a wide symmetric grid (midpoint-free Riemann sum as in var_state.py:88-91)
+    g2 = grid.Grid(np.array([8.0, 8.0]), 200)
+    dens = np.exp(-0.5 * (g2.coords ** 2).sum(-1)) / (2 * np.pi)
+    assert abs(g2.bin_area * dens.sum() - 1.0) < 1e-6
+
+
 def test_timings_and_cov_matrix():
     t = util.Timings()
     t.start_timing("a"); t.stop_timing("a")
