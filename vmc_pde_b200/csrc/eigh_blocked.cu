@@ -101,7 +101,7 @@ struct PanelArgs {
   int S;                   // owned slots per CTA (multiple of 4)
   double *d, *e, *tau;
   double* acol;            // [ld] updated pivot row
-  double* part;            // [2 nb + 2][grid] partial dot products
+  double* part;            // [2 nb + 2][grid][2] partial dot products as (value, sequence) messages
   double* psig;            // [grid]
   double* vrows;           // [nb][nb + 1]: v_k(j0 + ii), ii in [0, nb]
   double* wrows;           // [nb][nb + 1]: w_k(j0 + ii)
@@ -186,6 +186,7 @@ __global__ void __launch_bounds__(kPT, 1) tridiag_panel_kernel(const __grid_cons
     }
     if (have) {
       // ---------------- phase A: reflector, y = A22 v on the rows of this CTA, partial dots ----------------
+      const unsigned long long seq = (unsigned long long)j + 1;   // message tag of this column
       // one round trip for everything the reflector needs: norm partials and the raw pivot row
       const double sg = tid < G ? __ldcg(a.psig + tid) : 0.0;
       for (int c = tid; c < n; c += kPT) vs[c] = c > j ? __ldcg(a.acol + c) : 0.0;
@@ -376,14 +377,16 @@ __global__ void __launch_bounds__(kPT, 1) tridiag_panel_kernel(const __grid_cons
         const int k = tid < i ? tid : tid - i;
         double s = 0.0;
         for (int q = 0; q < S; ++q) s = fma(arr[q * ldo + k], vown[q], s);
-        a.part[(size_t)((tid < i ? 0 : nb) + k) * G + b] = s;
+        ll_store(a.part + 2 * ((size_t)((tid < i ? 0 : nb) + k) * G + b), s, seq);
       }
       if (tid < S) anext[tid] = anext_reg;
       yvp = bsum_(yvp, red);
-      if (tid == 0) a.part[(size_t)(2 * nb) * G + b] = yvp;
-      if (tid < S && row_of_slot(tid) == j + 1) a.part[(size_t)(2 * nb + 1) * G] = ys[tid];
+      if (tid == 0) ll_store(a.part + 2 * ((size_t)(2 * nb) * G + b), yvp, seq);
+      if (tid < S && row_of_slot(tid) == j + 1) ll_store(a.part + 2 * (size_t)(2 * nb + 1) * G, ys[tid], seq);
       VMC_PROF(3);
-      grid_sync(a.bar, target);
+      // The partial dots travel as (value, sequence) messages, so they need no barrier; the bulk column parts of the
+      // symmetric mat-vec do.
+      if (sym) grid_sync(a.bar, target);
       VMC_PROF(4);
       // ---------------- phase B: reduce the partials ----------------
       if (sym) {
@@ -412,25 +415,26 @@ __global__ void __launch_bounds__(kPT, 1) tridiag_panel_kernel(const __grid_cons
       {  // Value t of the 2 i + 1 reduced partials is summed by CTA t (warp 0, coalesced, fixed order) and published as
          // a (value, sequence) message; every CTA then collects all of them.  Two L2 round trips, no all-to-all reads.
         const int nred = 2 * i + 1;
-        const unsigned long long seq = (unsigned long long)j + 1;
         for (int t = b; t < nred; t += G) {
           if (warp == 0) {
             const int kk = t < i ? t : (t < 2 * i ? nb + (t - i) : 2 * nb);
-            const double* src = a.part + (size_t)kk * G;
+            const double* src = a.part + 2 * (size_t)kk * G;
             double sacc = 0.0;
-            for (int q = lane; q < G; q += 32) sacc += __ldcg(src + q);
+            for (int q = lane; q < G; q += 32) sacc += ll_load(src + 2 * q, seq);   // waits for CTA q's message
             sacc = wsum_(sacc);
             if (lane == 0) ll_store(a.totals + 2 * t, sacc, seq);
           }
         }
+        VMC_PROF(9);
+        if (tid == kPT - 1) red[41] = ll_load(a.part + 2 * (size_t)(2 * nb + 1) * G, seq);   // y at the next pivot row
         for (int t = tid; t < nred; t += kPT) {
           const double v = ll_load(a.totals + 2 * t, seq);
           if (t < i) PV[t] = v;
           else if (t < 2 * i) PWs[t - i] = v;
           else red[40] = v;
         }
+        VMC_PROF(10);
       }
-      if (tid == kPT - 1) red[41] = __ldcg(a.part + (size_t)(2 * nb + 1) * G);
     } else {
       // no reflector for the last two columns: d / e only, zero panel vectors
       if (b == 0 && tid == 0) {
@@ -677,7 +681,7 @@ size_t blocked_tridiag_scratch_bytes(int n, int ld) {
   BlockedPlan p;
   if (!plan_panel(n, &p)) return 0;
   const int nb = p.nb, G = p.grid;
-  return al256((size_t)ld * 8) + al256((size_t)(2 * nb + 2) * G * 8) + al256((size_t)G * 8) +
+  return al256((size_t)ld * 8) + al256((size_t)(2 * nb + 2) * G * 16) + al256((size_t)G * 8) +
          2 * al256((size_t)nb * (nb + 1) * 8) + 2 * al256((size_t)2 * nb * ld * 8) + al256((size_t)kBarCounters * kBarStride * 4) +
          al256((size_t)(2 * nb + 1) * 16) +
          (p.sym ? al256((size_t)G * ld * 8) : 0);
@@ -704,7 +708,7 @@ int tridiag_blocked(double* A, int n, int ld, double* d, double* e, double* tau,
   PanelArgs a{};
   a.A = A; a.ld = ld; a.n = n; a.nb = nb; a.S = p.S; a.d = d; a.e = e; a.tau = tau;
   a.acol = (double*)take((size_t)ld * 8);
-  a.part = (double*)take((size_t)(2 * nb + 2) * G * 8);
+  a.part = (double*)take((size_t)(2 * nb + 2) * G * 16);
   a.psig = (double*)take((size_t)G * 8);
   a.vrows = (double*)take((size_t)nb * (nb + 1) * 8);
   a.wrows = (double*)take((size_t)nb * (nb + 1) * 8);
@@ -731,8 +735,11 @@ int tridiag_blocked(double* A, int n, int ld, double* d, double* e, double* tau,
     a.j1 = a.j0 + nb;
     a.bar = bars;
     a.epoch0 = epoch;
-    epoch += 1;                          // barriers of this launch: prologue, then 2 per reflector column (1 for the last two)
-    for (int i = 0; i < a.nbp; ++i) epoch += (n - (a.j0 + i) - 1 >= 2) ? 2 : 1;
+    epoch += 1;   // barriers of this launch: prologue, one per column, one more per column in symmetric mode
+    for (int i = 0; i < a.nbp; ++i) {
+      const int m = n - (a.j0 + i) - 1;
+      epoch += (m >= 2 && a.Z != nullptr && m >= a.sym_min_m) ? 2 : 1;
+    }
     void* kargs[] = {(void*)&a};
     VMC_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)tridiag_panel_kernel, dim3(G), dim3(kPT), kargs, p.smem, s));
     if (a.j1 < n) {
@@ -748,12 +755,13 @@ int tridiag_blocked(double* A, int n, int ld, double* d, double* e, double* tau,
     cudaStreamSynchronize(s);
     cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost);
     cudaFree(prof);
-    const char* names[9] = {"A: loads + norm", "A: build v, writes", "A: mat-vec", "A: y, partial dots", "barrier 1",
-                            "B: gather + reduce", "B: scalars", "B: w, next pivot row", "barrier 2"};
+    const char* names[11] = {"A: loads + norm", "A: build v, writes", "A: mat-vec", "A: y, partial dots", "barrier 1",
+                             "B: rest of gather", "B: scalars", "B: w, next pivot row", "barrier 2",
+                             "B: sym gather + owner reduce", "B: collect totals"};
     long long tot = 0;
-    for (int k = 0; k < 9; ++k) tot += h[k];
+    for (int k = 0; k < 11; ++k) tot += h[k];
     fprintf(stderr, "[tridiag_panel_kernel n=%d] CTA 0 cycles per column by phase (total %.0f):\n", n, (double)tot / n);
-    for (int k = 0; k < 9; ++k) fprintf(stderr, "   %-24s %9.0f  %5.1f%%\n", names[k], (double)h[k] / n, 100.0 * h[k] / tot);
+    for (int k = 0; k < 11; ++k) fprintf(stderr, "   %-30s %9.0f  %5.1f%%\n", names[k], (double)h[k] / n, 100.0 * h[k] / tot);
   }
   return 0;
 }
