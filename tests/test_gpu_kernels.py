@@ -214,6 +214,17 @@ def test_eigh_against_lapack(L):
         assert np.abs(V.T @ V - np.eye(n)).max() < 1e-12
 
 
+def test_eigh_is_run_to_run_deterministic(L):
+    """Fixed-order reductions and tagged messages: two runs on the same matrix agree bit for bit (blocked path, both
+    mat-vec modes), and so do the replicated solves of a multi-GPU run."""
+    rng = np.random.default_rng(11)
+    for n in (700, 2053):
+        A = rng.normal(size=(n + 100, n)) * 10.0 ** (-4.0 * np.arange(n) / n); S = A.T @ A / (n + 100)
+        runs = [_eigh(L, S) for _ in range(3)]
+        for ev, V in runs[1:]:
+            assert np.array_equal(ev, runs[0][0]) and np.array_equal(V, runs[0][1])
+
+
 def test_solve_tail_and_cholesky_against_oracle(L):
     from vmc_pde_b200 import _lib
     rng = np.random.default_rng(3)

@@ -39,7 +39,9 @@ RHS_CASES = [(2, 4, 1, "no_add", "Gauss", "diffusion", 10000, np.zeros(2)),     
              (6, 4, 3, "different_add", "Gauss", "advection_hamiltonian_wDiss", 6000, np.array([1., 0, 0, 1, 0, 0])),  # 'harmonicOsc_diff', P = 411
              (8, 4, 4, "no_add", "Gauss", "diffusion", 5000, np.zeros(8)),                        # P = 364
              (4, 3, 6, "no_add", "Gauss", "diffusion_anisotropic", 3000, np.zeros(4)),
-             (2, 4, 2, "no_add", "Gauss", "advection_hamiltonian", 2000, np.ones(2))]              # 'harmonicOsc'
+             (2, 4, 2, "no_add", "Gauss", "advection_hamiltonian", 2000, np.ones(2)),              # 'harmonicOsc'
+             (2, 4, 85, "no_add", "Gauss", "diffusion", 4096, np.zeros(2))]                       # BASELINE C2 architecture, P = 2053:
+                                                                                                  # blocked eigensolver incl. the lower-triangle mode
 
 
 @pytest.mark.parametrize("d,depth,h,variant,latent,eqname,N,offset", RHS_CASES)

@@ -40,6 +40,17 @@ eq = evolutionEq.EvolutionEquation(dim=d, name="diffusion")
 T = tdvp.TDVP()
 upd, info = T(vs.get_parameters(), 0.0, psi=vs, evolutionEq=eq, nSamplesTDVP=N, nSamplesObs=N, timings=None)
 V = T.V   # collective when sharded
+# every rank must hold the same solve results (the scripts above only look at rank 0)
+fp = torch.stack([T.ev.sum(), T.ev[-1], upd.norm(), T.VtF.norm(), T.snr.norm(), T.invEv.sum(), T.solverResidual, T.tdvp_error,
+                  info["entropy"], info["max_grad"], V.abs().sum()]).to(torch.float64)
+if world > 1:
+    allfp = [torch.empty_like(fp) for _ in range(world)]
+    dist.all_gather(allfp, fp)
+    dev = max(float(((a - allfp[0]).abs() / (allfp[0].abs() + 1e-300)).max()) for a in allfp)
+    if rank == 0:
+        print("max relative deviation of the per-rank fingerprints:", dev, flush=True)
+        for r_, a in enumerate(allfp):
+            print("  rank", r_, [f"{float(x):.15e}" for x in a], flush=True)
 if rank == 0:
     torch.save({"update": upd.cpu(), "S0": T.S0.cpu(), "F0": T.F0.cpu(), "ev": T.ev.cpu(), "VtF": T.VtF.cpu(), "snr": T.snr.cpu(),
                 "res": T.solverResidual.cpu(), "err": T.tdvp_error.cpu(), "V": V.cpu(), "entropy": info["entropy"].cpu()}, args.out)

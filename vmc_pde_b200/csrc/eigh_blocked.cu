@@ -44,11 +44,6 @@ __device__ __forceinline__ double bsum_(double v, double* sh) {
   return wsum_(r);
 }
 
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 // Barrier over all CTAs of the (cooperative) grid.  148 same-address atomics serialise at L2 (~27 cycles each, ~4000
 // cycles per barrier on B200) and 148 x 148 flag polls hot-spot a handful of lines (measured: worse), so arrivals are
 // spread over 16 counters on separate 128-byte lines and one warp per CTA polls their sum.  Arrival is a release
@@ -76,16 +71,21 @@ __device__ __forceinline__ void grid_sync(unsigned* ctr, unsigned& epoch) {
   __syncthreads();
 }
 
-// 16-byte value + sequence-number message (the flag travels with the data, as in NCCL's LL protocol)
-__device__ __forceinline__ void ll_store(double* slot, double v, unsigned long long seq) {
-  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(__double_as_longlong(v)), "l"(seq) : "memory");
+// 16-byte message {value.lo, tag, value.hi, tag}: only 8-byte accesses are single-copy atomic, so each half of the
+// double travels with its own copy of the tag and the reader waits until both match (the line format of NCCL's LL
+// protocol).  A 16-byte (value, tag) pair can tear: the tag may arrive before the value.
+__device__ __forceinline__ void ll_store(double* slot, double v, unsigned tag) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(slot), "r"((unsigned)bits), "r"(tag),
+               "r"((unsigned)(bits >> 32)), "r"(tag)
+               : "memory");
 }
-__device__ __forceinline__ double ll_load(const double* slot, unsigned long long seq) {
-  unsigned long long v, sq;
+__device__ __forceinline__ double ll_load(const double* slot, unsigned tag) {
+  unsigned lo, t1, hi, t2;
   do {
-    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v), "=l"(sq) : "l"(slot) : "memory");
-  } while (sq != seq);
-  return __longlong_as_double((long long)v);
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(t1), "=r"(hi), "=r"(t2) : "l"(slot) : "memory");
+  } while (t1 != tag || t2 != tag);
+  return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
 }
 
 __device__ __forceinline__ int gcd16(int a) {  // gcd(a, 16) for a >= 1
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(kPT, 1) tridiag_panel_kernel(const __grid_cons
     }
     if (have) {
       // ---------------- phase A: reflector, y = A22 v on the rows of this CTA, partial dots ----------------
-      const unsigned long long seq = (unsigned long long)j + 1;   // message tag of this column
+      const unsigned seq = (unsigned)j + 1u;   // message tag of this column
       // one round trip for everything the reflector needs: norm partials and the raw pivot row
       const double sg = tid < G ? __ldcg(a.psig + tid) : 0.0;
       for (int c = tid; c < n; c += kPT) vs[c] = c > j ? __ldcg(a.acol + c) : 0.0;
