@@ -205,10 +205,24 @@ def run_ours(args):
     barrier()
     ms_e2e = t0.elapsed_time(t1)
     clk = clocks.stop() if rank == 0 else None
+    # ---- reported beside the headline, never instead of it: SExp as a matrix-free operator (TDVP(computeSExp="lazy")).
+    # The reference builds SExp every call (tdvp.py:47) although only AdaptiveHeun reads it, and only as v^T SExp v
+    # (stepper.py:71); FixedStepper never does.  Same step, one Gram out of three not formed.
+    T.computeSExp = "lazy"
+    step_device()
+    barrier()
+    tl0 = torch.cuda.Event(enable_timing=True); tl1 = torch.cuda.Event(enable_timing=True)
+    tl0.record()
+    for _ in range(2):
+        step_device()
+    tl1.record()
+    barrier()
+    ms_lazy = tl0.elapsed_time(tl1) / 2
+    T.computeSExp = True
     if world > 1:
-        t = torch.tensor([ms, ms_e2e], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms, ms_e2e, ms_lazy], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
+        ms, ms_e2e, ms_lazy = float(t[0]), float(t[1]), float(t[2])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -239,6 +253,9 @@ def run_ours(args):
                      "share_of_step": sum(gram_ms) / ms if gram_ms else None},
         "stages_ms_per_rhs": {"gram": sum(gram_ms) / max(len(eigh_ms), 1), "eigh": sum(eigh_ms) / max(len(eigh_ms), 1),
                               "everything_else": (ms - sum(gram_ms) - sum(eigh_ms)) / max(len(eigh_ms), 1)},
+        "variants": {"lazy_SExp_steps_per_s": 1e3 / ms_lazy,
+                     "note": "TDVP(computeSExp='lazy'): SExp kept as a matrix-free operator on the resident O (2 Grams per RHS "
+                             "instead of 3); not the headline -- the reference forms SExp every call"},
         "last_entropy": ent,
     }
     # CPU arm: rank 0 at N=1 only (under torchrun the host threads are pinned to 1 per rank; see --impl reference)

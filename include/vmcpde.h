@@ -139,6 +139,12 @@ int vmcpde_center_force(double* O, int64_t n, int64_t ldo, const double* meanO, 
  * leading dimension ldo >= Pp with zero padding columns.  n must be a multiple of 16. */
 int vmcpde_gram(const double* O, int64_t n, int64_t ldo, int32_t Pp, int32_t n_mats,
                 const double* const* weights, double* const* S, vmcpde_stream stream);
+/* Matrix-free product with a weighted Gram: out[c] += sum_i w[i] (O[i,:] . v) O[i,c] = ((O^T diag(w) O) v)[c], two
+ * streaming passes over O instead of the N P^2 flops of the matrix.  The reference reads SExp (tdvp.py:47) only through
+ * normFunction(v, SExp) (stepper.py:71; main.py:24-26: v^T S v), which this serves without building SExp.
+ * w may be NULL (w = 1); v, out: ldo doubles; t: n doubles of scratch; workspace: vmcpde_moments_workspace_bytes. */
+int vmcpde_gram_matvec(const double* O, int64_t n, int64_t ldo, const double* w, const double* v, double* t,
+                       double* out, void* workspace, size_t workspace_bytes, vmcpde_stream stream);
 /* S <- scale * S on the upper triangle, mirrored to the lower; then, if shift > 1e-10,
  * S += diag(shift * diag(S)) (tdvp.py:50-51).  S_shifted may alias S or be a second Pp x Pp buffer. */
 int vmcpde_sym_finalize(double* S, int32_t Pp, double scale, vmcpde_stream stream);

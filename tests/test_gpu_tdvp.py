@@ -170,6 +170,40 @@ def test_observable_resampling_and_student_t():
     assert torch.isfinite(upd).all() and float(T.ev[-1]) > 0
 
 
+def test_lazy_sexp_operator_matches_the_matrix():
+    """TDVP(computeSExp="lazy"): SExp as a matrix-free operator (stepper.py:71 only needs v^T SExp v) equals the eagerly
+    built matrix, in the quadratic form, entry by entry once materialised, and through a whole AdaptiveHeun step."""
+    from vmc_pde_b200 import tdvp, stepper
+    smp, vs, eq, spec = build(6, 4, 3, "different_add", "Gauss", "advection_hamiltonian_wDiss", np.array([1., 0, 0, 1, 0, 0]))
+    theta = vs.get_parameters().clone()
+    key0 = vs.sampler.key.copy()
+    outs = {}
+    for mode in (True, "lazy"):
+        vs.sampler.key = key0.copy(); vs.set_parameters(theta)
+        T = tdvp.TDVP(computeSExp=mode)
+        upd, info = T(theta, 0.0, psi=vs, evolutionEq=eq, nSamplesTDVP=4000, nSamplesObs=4000, timings=None)
+        v = torch.linspace(-1, 1, vs.numParameters, device=upd.device, dtype=torch.float64)
+        outs[mode] = (upd.clone(), float(norm_fun(v, T.SExp)), (T.SExp @ v).clone(), T)
+    assert isinstance(outs["lazy"][3].SExp, tdvp.LazyGram) and torch.equal(outs[True][0], outs["lazy"][0])
+    assert abs(outs["lazy"][1] / outs[True][1] - 1) < 1e-12 and relerr(outs["lazy"][2], outs[True][2]) < 1e-12
+    assert relerr(outs["lazy"][3].SExp.materialize(), outs[True][3].SExp) < 1e-12
+    res = {}
+    for mode in (True, "lazy"):
+        vs.sampler.key = key0.copy(); vs.set_parameters(theta)
+        T = tdvp.TDVP(computeSExp=mode)
+        ah = stepper.AdaptiveHeun(timeStep=1e-3, tol=1e-4, maxStep=1e-2)
+        y, dt, _ = ah.step(0, T, theta, evolutionEq=eq, psi=vs, nSamplesTDVP=3000, nSamplesObs=3000, normFunction=norm_fun, timings=None)
+        res[mode] = (y.clone(), dt, ah.dt)
+    assert relerr(res["lazy"][0], res[True][0]) < 1e-12 and res["lazy"][1] == res[True][1] and abs(res["lazy"][2] / res[True][2] - 1) < 1e-9
+    # a stale operator (its O buffer has been overwritten by a later right-hand side) refuses to answer
+    T = tdvp.TDVP(computeSExp="lazy")
+    T(theta, 0.0, psi=vs, evolutionEq=eq, nSamplesTDVP=2000, nSamplesObs=2000, timings=None)
+    old = T.SExp
+    T(theta, 0.0, psi=vs, evolutionEq=eq, nSamplesTDVP=2000, nSamplesObs=2000, timings=None)
+    with pytest.raises(RuntimeError):
+        old.dot(torch.ones(vs.numParameters, device="cuda", dtype=torch.float64))
+
+
 def test_shifted_cholesky_extension_and_errors():
     from vmc_pde_b200 import tdvp
     smp, vs, eq, spec = build(6, 4, 3, "no_add", "Gauss", "diffusion", np.zeros(6))

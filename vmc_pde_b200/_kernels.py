@@ -177,6 +177,14 @@ def center_force(O, n, ldo, meanO, eloc, logp_, meanE, dE, wE, wLp, Fsum, var_su
                                                _lib.ptr(var_sum), _lib.ptr(ws), ws.numel() * 8, _lib.stream()))
 
 
+def gram_matvec(O, n, ldo, w, v, t, out):
+    """out += (O^T diag(w) O) v without forming the matrix (v, out: ldo entries; t: n scratch)."""
+    _count(3)
+    ws = _moments_ws(n, ldo)
+    _lib.check(_lib.load().vmcpde_gram_matvec(_lib.ptr(O), int(n), int(ldo), _lib.ptr(w), _lib.ptr(v), _lib.ptr(t), _lib.ptr(out),
+                                              _lib.ptr(ws), ws.numel() * 8, _lib.stream()))
+
+
 def gram(O, n, ldo, Pp, weights, mats):
     """mats[m] += sum_i weights[m][i] O[i]^T O[i] on the upper-triangular tiles; n multiple of 16."""
     _count(1)

@@ -27,13 +27,15 @@ __device__ __forceinline__ double block_reduce_sum(double v, double* sh) {
 }
 
 // Row-block streaming pass over O (every row is read as one contiguous run: HBM-friendly), two-level fixed-order
-// reduction:  CENTER = false:  part[rb][c] = sum_{i in block rb} O[i][c]
-//             CENTER = true :  O[i][c] -= meanO[c];  part[rb][c] = sum_{i in block rb} (E[i] - meanE) * O[i][c]
+// reduction:  MODE 0        :  part[rb][c] = sum_{i in block rb} O[i][c]
+//             MODE 1 (CENTER):  O[i][c] -= meanO[c];  part[rb][c] = sum_{i in block rb} (E[i] - meanE) * O[i][c]
 // grid = (column tiles of 4096, row blocks of 512); ldo must be even.
-template <bool CENTER>
+//             MODE 2        :  part[rb][c] = sum_{i in block rb} eloc[i] * O[i][c]          (eloc = any per-row factor)
+template <int MODE>
 __global__ void __launch_bounds__(kRT)
 rowblock_kernel(double* __restrict__ O, long long n, long long ldo, const double* __restrict__ meanO,
                 const double* __restrict__ eloc, double meanE, double* __restrict__ part) {
+  constexpr bool CENTER = MODE == 1;
   const long long c0 = (long long)blockIdx.x * kTileCols + 2 * threadIdx.x;
   const long long i0 = (long long)blockIdx.y * kRowsPerCta;
   const long long i1 = min(n, i0 + kRowsPerCta);
@@ -61,6 +63,10 @@ rowblock_kernel(double* __restrict__ O, long long n, long long ldo, const double
         if (in[k]) *(double2*)(row + k * 2 * kRT) = v[k];
         acc[k].x = fma(de, v[k].x, acc[k].x); acc[k].y = fma(de, v[k].y, acc[k].y);
       }
+    } else if (MODE == 2) {
+      const double f = __ldg(eloc + i);
+#pragma unroll
+      for (int k = 0; k < kKC; ++k) { acc[k].x = fma(f, v[k].x, acc[k].x); acc[k].y = fma(f, v[k].y, acc[k].y); }
     } else {
 #pragma unroll
       for (int k = 0; k < kKC; ++k) { acc[k].x += v[k].x; acc[k].y += v[k].y; }
@@ -84,6 +90,32 @@ rowblock_kernel(double* __restrict__ O, long long n, long long ldo, const double
 #pragma unroll
   for (int k = 0; k < kKC; ++k)
     if (in[k]) *(double2*)(out + k * 2 * kRT) = acc[k];
+}
+
+// t[i] = w[i] * sum_c O[i][c] v[c]   (warp per row, v through L1; w may be NULL)
+__global__ void __launch_bounds__(256) rowdot_kernel(const double* __restrict__ O, long long n, long long ldo, int cols,
+                                                     const double* __restrict__ w, const double* __restrict__ v,
+                                                     double* __restrict__ t) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (long long i = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += (long long)gridDim.x * wpb) {
+    const double* row = O + i * ldo;
+    double s0 = 0.0, s1 = 0.0;
+    int c = 2 * lane;
+    for (; c + 64 < cols; c += 128) {
+      const double2 a = *(const double2*)(row + c), b = *(const double2*)(row + c + 64);
+      const double2 x = __ldg((const double2*)(v + c)), y = __ldg((const double2*)(v + c + 64));
+      s0 = fma(a.x, x.x, s0); s0 = fma(a.y, x.y, s0); s1 = fma(b.x, y.x, s1); s1 = fma(b.y, y.y, s1);
+    }
+    if (c < cols) {
+      const double2 a = *(const double2*)(row + c);
+      const double2 x = __ldg((const double2*)(v + c));
+      s0 = fma(a.x, x.x, s0); s0 = fma(a.y, x.y, s0);
+    }
+    double sum = s0 + s1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) t[i] = w ? w[i] * sum : sum;
+  }
 }
 
 // dst[c] += sum_rb part[rb][c]  (fixed order)
@@ -189,7 +221,7 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_moments1(const doub
     VMC_REQUIRE(workspace && workspace_bytes >= need, "vmcpde_moments1: workspace too small");
     const int row_blocks = (int)((n + kRowsPerCta - 1) / kRowsPerCta);
     const dim3 grid((unsigned)((ldo + kTileCols - 1) / kTileCols), (unsigned)row_blocks);
-    rowblock_kernel<false><<<grid, kRT, 0, s>>>(const_cast<double*>(O), n, ldo, nullptr, nullptr, 0.0, (double*)workspace);
+    rowblock_kernel<0><<<grid, kRT, 0, s>>>(const_cast<double*>(O), n, ldo, nullptr, nullptr, 0.0, (double*)workspace);
     colsum_partials_kernel<<<(unsigned)((ldo + 255) / 256), 256, 0, s>>>((const double*)workspace, row_blocks, ldo, sums + 4);
   }
   scalar_moments_kernel<<<1, 1024, 0, s>>>(eloc, logp, n, sums);
@@ -213,10 +245,36 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_center_force(double
   cudaStream_t s = (cudaStream_t)stream;
   const int row_blocks = (int)((n + kRowsPerCta - 1) / kRowsPerCta);
   const dim3 grid((unsigned)((ldo + kTileCols - 1) / kTileCols), (unsigned)row_blocks);
-  rowblock_kernel<true><<<grid, kRT, 0, s>>>(O, n, ldo, meanO, eloc, meanE, (double*)workspace);
+  rowblock_kernel<1><<<grid, kRT, 0, s>>>(O, n, ldo, meanO, eloc, meanE, (double*)workspace);
   colsum_partials_kernel<<<(unsigned)((ldo + 255) / 256), 256, 0, s>>>((const double*)workspace, row_blocks, ldo, Fsum);
   sample_weights_kernel<<<1, 1024, 0, s>>>(eloc, logp, n, meanE, dE, wE, wLp, var_sum);
   VMC_LAUNCH_CHECK("center_force");
+  return 0;
+}
+
+// Matrix-free product with a weighted Gram: out[c] += sum_i w[i] (O[i,:] . v) O[i,c], i.e. out += (O^T diag(w) O) v without
+// forming the P x P matrix (two streaming passes over O instead of N P^2 flops).  Used for quadratic forms with SExp
+// (stepper.py:71 reads SExp only through normFunction(v, SExp)).  v, out: ldo doubles (v zero in the padding columns);
+// t: n doubles of scratch; workspace as vmcpde_moments1.
+extern "C" __attribute__((visibility("default"))) int vmcpde_gram_matvec(const double* O, int64_t n, int64_t ldo, const double* w, const double* v,
+                                                                        double* t, double* out, void* workspace,
+                                                                        size_t workspace_bytes, vmcpde_stream stream) {
+  using namespace vmc;
+  VMC_REQUIRE(O && v && t && out, "vmcpde_gram_matvec: null pointer");
+  if (n <= 0) return 0;
+  VMC_REQUIRE(ldo % 2 == 0 && ((uintptr_t)O & 15) == 0 && ((uintptr_t)v & 15) == 0, "vmcpde_gram_matvec: O / v must be 16-byte aligned with an even ldo");
+  size_t need = 0;
+  vmcpde_moments_workspace_bytes(n, ldo, &need);
+  VMC_REQUIRE(workspace && workspace_bytes >= need, "vmcpde_gram_matvec: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long want_blocks = (long long)((n + 7) / 8);
+  const int blocks = (int)(want_blocks < (long long)num_sms() * 8 ? want_blocks : (long long)num_sms() * 8);
+  rowdot_kernel<<<blocks, 256, 0, s>>>(O, n, ldo, (int)ldo, w, v, t);
+  const int row_blocks = (int)((n + kRowsPerCta - 1) / kRowsPerCta);
+  const dim3 grid((unsigned)((ldo + kTileCols - 1) / kTileCols), (unsigned)row_blocks);
+  rowblock_kernel<2><<<grid, kRT, 0, s>>>(const_cast<double*>(O), n, ldo, nullptr, t, 0.0, (double*)workspace);
+  colsum_partials_kernel<<<(unsigned)((ldo + 255) / 256), 256, 0, s>>>((const double*)workspace, row_blocks, ldo, out);
+  VMC_LAUNCH_CHECK("gram_matvec");
   return 0;
 }
 

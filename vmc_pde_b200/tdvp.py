@@ -22,6 +22,73 @@ import torch
 from . import _kernels, mpi_wrapper as mpi, global_defs
 
 
+class LazyGram:
+    """SExp = (1/N) sum_i logp_i^2 dO_i dO_i^T (tdvp.py:47) as an operator on the centred O that is still resident.
+
+    The reference reads SExp only through `normFunction(v, SExp)` (stepper.py:71; main.py:24-26: v^T S v), which needs
+    S.dot(v) -- two streaming passes over O (`vmcpde_gram_matvec`) instead of the N P^2 flops of the matrix.  `S.dot(v)`,
+    `S @ v` and `v @ S` are matrix free; anything that needs the entries (`materialize()`, indexing, `.cpu()`) builds the
+    P x P matrix once with the Gram kernel and caches it.  Valid until the owning TDVP evaluates its next right-hand side
+    (the O buffer is reused); using it later raises.  With several ranks `dot` and `materialize` are collective."""
+
+    def __init__(self, owner, gen, O, n, n_pad, Pp, P, w, N):
+        self._owner, self._gen, self._O, self._n, self._n_pad = owner, gen, O, n, n_pad
+        self._Pp, self._P, self._w, self._N = Pp, P, w, N
+        self._t = None
+        self._mat = None
+        self.shape = (P, P)
+        self.dtype, self.device = O.dtype, O.device
+
+    def _alive(self):
+        if self._gen is not None and self._owner._gen != self._gen:
+            raise RuntimeError("this SExp refers to the samples of an earlier right-hand side (the O buffer has been reused); "
+                               "read it before the next TDVP call or use TDVP(computeSExp=True)")
+
+    def dot(self, v):
+        if self._mat is not None:
+            return self._mat @ _kernels.as_dev(v)
+        self._alive()
+        vp = _kernels.zeros(self._Pp)
+        vp[:self._P] = _kernels.as_dev(v).reshape(-1)
+        out = _kernels.zeros(self._Pp)
+        if self._t is None:
+            self._t = _kernels.empty(max(self._n, 1))
+        _kernels.gram_matvec(self._O, self._n, self._Pp, self._w, vp, self._t, out)
+        mpi.allreduce_(out)
+        return out[:self._P] / self._N
+
+    __matmul__ = dot
+
+    def __rmatmul__(self, v):  # v @ S: S is symmetric
+        return self.dot(v)
+
+    @property
+    def T(self):
+        return self
+
+    def materialize(self):
+        if self._mat is None:
+            self._alive()
+            M = _kernels.zeros(self._Pp, self._Pp)
+            if self._n_pad > self._n:
+                self._w[self._n:self._n_pad].zero_()
+            _kernels.gram(self._O, self._n_pad, self._Pp, self._Pp, [self._w], [M])
+            mpi.allreduce_(M)
+            _kernels.sym_finalize(M, self._Pp, 1.0 / self._N)
+            self._mat = M[:self._P, :self._P]
+        return self._mat
+
+    def __getitem__(self, idx):
+        return self.materialize()[idx]
+
+    def cpu(self):
+        return self.materialize().cpu()
+
+    def __array__(self, dtype=None):
+        a = self.materialize().cpu().numpy()
+        return a.astype(dtype) if dtype is not None else a
+
+
 def solve_shard_range(Pp, world, rank):
     """Eigenvector slice [row0, row0 + nrows) of rank `rank` in a sharded solve: the Pp / 128 blocks of 128 eigenvectors
     are dealt contiguously; ranks beyond the block count get an empty slice."""
@@ -39,7 +106,8 @@ class TDVP:
     diagonalizeOnDevice: bool = False   # kept for signature parity; the solve is always on the device
     # ---- extensions (not in the reference; defaults reproduce the reference's semantics) ----
     solver: str = "eigh"               # "eigh" | "cholesky" (needs diagonalShift > 0; no ev / V / snr)
-    computeSExp: bool = True           # SExp is only read by AdaptiveHeun (stepper.py:71)
+    computeSExp: object = True         # True: build SExp every call (the reference, tdvp.py:47); "lazy": SExp is an
+                                       # operator on the resident O (LazyGram; stepper.py:71 only needs v^T SExp v); False: skip
     computeSNR: bool = True            # snr is logged by main.py:187 and gates the solve when useSNR
     shardSolve: bool = True            # several ranks: shard the post-tridiagonal O(P^3) stages over eigenvectors
     chunkSamples: int = 0              # samples per chunk (0 = choose from free memory)
@@ -51,6 +119,9 @@ class TDVP:
         self._bufP = None
         self._P = None
         self._vt_range = None
+        self._gen = 0              # bumped whenever the O buffer is about to be overwritten
+        self._lazy_ok = False      # the whole rank-local O is resident after pass 2 (one chunk)
+        self._lazy_src = self._lazy_gen = None
         self.S = self.S0 = self.F0 = self.SExp = self.ev = self.VtF = None
         self.rhoVar = self.snr = self.invEv = None
         self.solverResidual = self.tdvp_error = None
@@ -104,7 +175,7 @@ class TDVP:
             O[n:n_pad].zero_(); wE[n:n_pad].zero_(); wLp[n:n_pad].zero_()
         _kernels.center_force(O, n, ldo, meanO, E, lp, meanE, dE, wE, wLp, Fsum, var_sum)
         mats, weights = [S0], [None]
-        if self.computeSExp:
+        if self.computeSExp is True or (self.computeSExp and not self._lazy_ok):
             mats.append(SExp); weights.append(wLp)
         if self.computeSNR and self.solver == "eigh":
             mats.append(CEO); weights.append(wE)
@@ -116,7 +187,8 @@ class TDVP:
         mpi.allreduce_(self._second)
         inv = 1.0 / N
         _kernels.sym_finalize(S0, Pp, inv)
-        if self.computeSExp:
+        eager_sexp = self.computeSExp is True or (self.computeSExp and not self._lazy_ok)
+        if eager_sexp:
             _kernels.sym_finalize(SExp, Pp, inv)
         use_ceo = self.computeSNR and self.solver == "eigh"
         if use_ceo:
@@ -124,7 +196,13 @@ class TDVP:
         F = Fsum * inv
         self.ElocVar = (var_sum[0] * inv).clone()
         self.S0, self.F0 = S0[:P, :P], F[:P]
-        self.SExp = SExp[:P, :P] if self.computeSExp else None
+        if eager_sexp:
+            self.SExp = SExp[:P, :P]
+        elif self.computeSExp:
+            O, n, n_pad, w = self._lazy_src
+            self.SExp = LazyGram(self, self._lazy_gen, O, n, n_pad, Pp, P, w, N)
+        else:
+            self.SExp = None
         S = S0
         if self.diagonalShift > 1e-10:  # tdvp.py:50-51
             if self._Sshift is None:
@@ -206,6 +284,7 @@ class TDVP:
         mpi.allreduce_(first)
         self._set_first(first, N, P)
         scratch = (_kernels.zeros(n_pad), _kernels.zeros(n_pad), _kernels.zeros(n_pad))
+        self._lazy_ok, self._lazy_src, self._lazy_gen = True, (O, n, n_pad, scratch[2]), None   # this O is private: never reused
         self._pass2_chunk(E, lp, O, n, n_pad, Pp, Pp, (first[4:] / N).contiguous(), float(first[0]) / N, scratch)
         return self._finish(P, Pp, N, first)
 
@@ -286,6 +365,13 @@ class TDVP:
         eq = evolutionEq.equation_struct(t)
         self._buffers(P, Pp).zero_()
         rows, stored = self._plan_chunks(n_local, Pp)
+        self._gen += 1
+        self._lazy_ok = stored and n_local > 0
+        if self.computeSExp and self.computeSExp is not True and mpi.comm.Get_size() > 1:
+            # LazyGram.dot is collective: every rank must take the same branch
+            flag = torch.tensor([1.0 if self._lazy_ok else 0.0], dtype=torch.float64, device=global_defs.device())
+            mpi.allreduce_(flag)
+            self._lazy_ok = bool(flag.item() == mpi.comm.Get_size())
         if getattr(self, "_Obuf", None) is None or self._Obuf.shape != (rows, Pp):
             self._Obuf = None
             self._Obuf = _kernels.zeros(rows, Pp)
@@ -333,6 +419,7 @@ class TDVP:
                               self._scratch)
             toc("solve TDVP eqn.", t0)
         t0 = tic()
+        self._lazy_src, self._lazy_gen = (O, n_local, _kernels.round_up(max(n_local, 1), 16), self._scratch[2]), self._gen
         update = self._finish(P, Pp, N, first)
         toc("solve TDVP eqn.", t0)
         return update, x_all, lp_all, E_all
