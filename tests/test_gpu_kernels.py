@@ -214,6 +214,34 @@ def test_eigh_against_lapack(L):
         assert np.abs(V.T @ V - np.eye(n)).max() < 1e-12
 
 
+def test_eigh_blocked_path_edge_cases(L):
+    """Blocked path (n >= 384): reflector-free columns (diagonal / zero / block-diagonal input), the size thresholds of the
+    two mat-vec modes, sizes that are not multiples of the 4-row ownership chunks or of the 64-column panels, a spectrum
+    graded over 24 decades, tiny and huge overall scales."""
+    rng = np.random.default_rng(7)
+
+    def check(S, tol_res=3e-13):
+        n = S.shape[0]
+        ev, V = _eigh(L, S)
+        ref = np.linalg.eigvalsh(S); nrm = max(np.abs(ref).max(), 1e-300)
+        assert np.all(np.isfinite(ev)) and np.all(np.isfinite(V)) and np.all(np.diff(ev) >= 0)
+        assert np.abs(ev - ref).max() <= 2e-13 * nrm + 1e-300
+        assert np.abs(S @ V - V * ev).max() <= tol_res * nrm + 1e-300
+        assert np.abs(V.T @ V - np.eye(n)).max() < 2e-12
+
+    check(np.diag(rng.normal(size=600)))                      # every column has sigma == 0 (tau = 0)
+    check(np.zeros((400, 400)))
+    check(np.eye(450) * 3.0)
+    B = np.zeros((700, 700)); A = rng.normal(size=(300, 300)); B[:300, :300] = A + A.T; B[300:, 300:] = np.diag(rng.normal(size=400))
+    check(B)                                                  # dense block followed by reflector-free columns
+    for n in (384, 447, 449, 513, 1535, 1537, 1601):          # panel / chunk / mode boundaries (sym mode from a trailing size of 1536)
+        A = rng.normal(size=(n, n)); check((A + A.T) / 2)
+    n = 900
+    cs = 10.0 ** (-12.0 * np.arange(n) / n); A = rng.normal(size=(2 * n, n)) * cs; check(A.T @ A / (2 * n))   # 24 decades
+    A = rng.normal(size=(500, 500)); S = (A + A.T) / 2
+    check(S * 1e-150); check(S * 1e150)
+
+
 def test_eigh_is_run_to_run_deterministic(L):
     """Fixed-order reductions and tagged messages: two runs on the same matrix agree bit for bit (blocked path, both
     mat-vec modes), and so do the replicated solves of a multi-GPU run."""

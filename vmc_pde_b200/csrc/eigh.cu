@@ -17,6 +17,44 @@
 namespace vmc {
 
 // ================================================================================================
+// Stage 0: scaling (the role of dlascl in LAPACK's dsyevd / dstedc): S is multiplied by the power of two that brings its
+// largest entry into [0.5, 1) and the eigenvalues are scaled back at the end.  It keeps the squared norms of the
+// Householder step in range and gives the divide & conquer deflation test a matrix of norm O(1).
+// Everything stays on the device: sc[0] = max |S|, sc[1] = factor, sc[2] = 1 / factor.
+// ================================================================================================
+__global__ void __launch_bounds__(256) absmax_kernel(const double* __restrict__ S, int n, int ld, double* __restrict__ sc) {
+  double m = 0.0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)n * ld; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % ld);
+    if (c < n) m = fmax(m, fabs(S[i]));   // NaN entries are ignored here and surface in the result
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.0)
+    atomicMax((unsigned long long*)sc, (unsigned long long)__double_as_longlong(m));  // monotone for non-negative doubles
+}
+__global__ void scale_factor_kernel(double* __restrict__ sc) {
+  // max |S| * factor in [0.5, 1): exact (power of two), and the tridiagonal matrix enters divide & conquer with norm O(1)
+  // like LAPACK's dstedc -- the deflation tolerance 8 eps max(|d|, |z|) compares eigenvalues with components of unit
+  // vectors and over-deflates a matrix of small norm otherwise.
+  const double anrm = sc[0];
+  double f = 1.0;
+  if (anrm > 0.0 && anrm < 1.7e308) {
+    int e = 0;
+    frexp(anrm, &e);
+    e = max(-1000, min(1000, e));
+    f = scalbn(1.0, -e);
+  }
+  sc[1] = f;
+  sc[2] = 1.0 / f;
+}
+__global__ void __launch_bounds__(256) scale_by_kernel(double* __restrict__ x, size_t count, const double* __restrict__ factor) {
+  const double f = *factor;
+  if (f == 1.0) return;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) x[i] *= f;
+}
+
+// ================================================================================================
 // Stage 1: tridiagonalisation (full symmetric storage, row-major, leading dimension ld)
 // ================================================================================================
 __device__ __forceinline__ double warp_sum(double v) {
@@ -633,7 +671,7 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_eigh_workspace_byte
   const size_t rows = blocked ? (size_t)(n + 127) / 128 * 128 : (size_t)n;
   b += 2 * align_up(rows * ld * 8, 256);                // QT ping buffer, U
   if (blocked) b += align_up(blocked_tridiag_scratch_bytes(n, ld), 256) + align_up(blocked_backtransform_scratch_bytes(n, ld), 256);
-  b += 17 * align_up((size_t)(n + 8) * 8, 256);          // double vectors
+  b += 18 * align_up((size_t)(n + 8) * 8, 256);          // double vectors
   b += 8 * align_up((size_t)(n + 8) * 4, 256);           // int vectors
   b += align_up((size_t)(n + 8) * sizeof(DcRot), 256);  // rotations
   *bytes = b;
@@ -644,7 +682,7 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_eigh_workspace_byte
 extern "C" __attribute__((visibility("default"))) int vmcpde_eigh_launch_count(int32_t n, int32_t ld, int32_t* count) {
   VMC_REQUIRE(count && n >= 1 && ld >= n, "vmcpde_eigh_launch_count: bad arguments");
   const int depth = dc_tree_depth(n);
-  int c = 1 + 10 * depth;  // dc_init + per-level kernels
+  int c = 4 + 1 + 10 * depth;  // scaling (3 + 1), dc_init, per-level kernels
   if (blocked_eigh_supported(n, ld)) c += blocked_tridiag_launches(n) + blocked_backtransform_launches(n);
   else c += (n >= 3 ? 3 + 3 * (n - 3) + 1 : 0) + 1 + 1;
   *count = c;
@@ -687,8 +725,14 @@ static int eigh_impl(double* S, int32_t n, int32_t ld, double* ev, double* VT, i
   const bool timing = getenv("VMCPDE_EIGH_TIMING") != nullptr;
   cudaEvent_t evt[4];
   if (timing) { for (auto& e_ : evt) cudaEventCreate(&e_); cudaEventRecord(evt[0], s); }
-  // ---- stage 1
+  // ---- stage 0
   const int sms = num_sms();
+  double* sc = dvec();
+  VMC_CUDA_CHECK(cudaMemsetAsync(sc, 0, 3 * sizeof(double), s));
+  absmax_kernel<<<sms * 8, 256, 0, s>>>(S, n, ld, sc);
+  scale_factor_kernel<<<1, 1, 0, s>>>(sc);
+  scale_by_kernel<<<sms * 8, 256, 0, s>>>(S, (size_t)n * ld, sc + 1);
+  // ---- stage 1
   if (blocked) {
     if (int rc = tridiag_blocked(S, n, ld, d, e, tau, tri_scratch, tri_bytes, s)) return rc;
   } else if (n >= 3) {
@@ -749,6 +793,7 @@ static int eigh_impl(double* S, int32_t n, int32_t ld, double* ev, double* VT, i
     double* tl = b.lam; b.lam = b.lam_new; b.lam_new = tl;
   }
   VMC_CUDA_CHECK(cudaMemcpyAsync(ev, b.lam, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
+  scale_by_kernel<<<max(1, min(sms, (n + 255) / 256)), 256, 0, s>>>(ev, (size_t)n, sc + 2);
 
   if (timing) cudaEventRecord(evt[2], s);
   // ---- stage 3 (out of place: ZT = b.QT -> VT; if they alias, stage through the other buffer)
