@@ -23,7 +23,10 @@ if args.compare:
     print("update S-norm rel diff", sn)
     Va, Vb = a["V"], b["V"]
     print("|S V - V ev| (sharded V)", float((S0 @ Vb - Vb * b["ev"]).abs().max() / a["ev"][-1]))
-    ok = rel(b["S0"], a["S0"]) < 1e-11 and rel(b["ev"], a["ev"]) < 1e-11 and sn < 1e-14 and abs(float(a["err"]) - float(b["err"])) < 1e-10
+    print("v^T SExp v: 1 rank eager", a["q_eager"], "lazy", a["q_lazy"], "| R ranks eager", b["q_eager"], "lazy", b["q_lazy"],
+          "| lazy update == eager update:", bool(torch.equal(a["upd_lazy"], a["update"])), bool(torch.equal(b["upd_lazy"], b["update"])))
+    ql = max(abs(a["q_lazy"] / a["q_eager"] - 1), abs(b["q_lazy"] / b["q_eager"] - 1), abs(b["q_eager"] / a["q_eager"] - 1))
+    ok = ql < 1e-11 and rel(b["S0"], a["S0"]) < 1e-11 and rel(b["ev"], a["ev"]) < 1e-11 and sn < 1e-14 and abs(float(a["err"]) - float(b["err"])) < 1e-10
     print("MULTI-GPU CHECK", "OK" if ok else "FAILED")
     sys.exit(0 if ok else 1)
 import torch.distributed as dist
@@ -38,8 +41,16 @@ smp = sampler.Sampler(dim=d, numChains=30, name="Gauss", mcmc_info={"offset": of
 vs = var_state.VarState(smp, d, 1, depth, network_args={"intmediate": (h,), "offset": off, "latentSpaceName": "Gauss", "dim": d})
 eq = evolutionEq.EvolutionEquation(dim=d, name="diffusion")
 T = tdvp.TDVP()
-upd, info = T(vs.get_parameters(), 0.0, psi=vs, evolutionEq=eq, nSamplesTDVP=N, nSamplesObs=N, timings=None)
+KEY0, THETA0 = vs.sampler.key.copy(), vs.get_parameters().clone()
+upd, info = T(THETA0, 0.0, psi=vs, evolutionEq=eq, nSamplesTDVP=N, nSamplesObs=N, timings=None)
 V = T.V   # collective when sharded
+# SExp through the quadratic form: eager matrix vs the matrix-free operator (collective with several ranks)
+vq = torch.linspace(-1, 1, vs.numParameters, device=upd.device, dtype=torch.float64)
+q_eager = float(vq @ T.SExp @ vq)
+T2 = tdvp.TDVP(computeSExp="lazy")
+vs.sampler.key = KEY0.copy()   # same samples for the second evaluation
+upd2, _ = T2(THETA0, 0.0, psi=vs, evolutionEq=eq, nSamplesTDVP=N, nSamplesObs=N, timings=None)
+q_lazy = float(vq @ T2.SExp @ vq)
 # every rank must hold the same solve results (the scripts above only look at rank 0)
 fp = torch.stack([T.ev.sum(), T.ev[-1], upd.norm(), T.VtF.norm(), T.snr.norm(), T.invEv.sum(), T.solverResidual, T.tdvp_error,
                   info["entropy"], info["max_grad"], V.abs().sum()]).to(torch.float64)
@@ -53,7 +64,8 @@ if world > 1:
             print("  rank", r_, [f"{float(x):.15e}" for x in a], flush=True)
 if rank == 0:
     torch.save({"update": upd.cpu(), "S0": T.S0.cpu(), "F0": T.F0.cpu(), "ev": T.ev.cpu(), "VtF": T.VtF.cpu(), "snr": T.snr.cpu(),
-                "res": T.solverResidual.cpu(), "err": T.tdvp_error.cpu(), "V": V.cpu(), "entropy": info["entropy"].cpu()}, args.out)
+                "res": T.solverResidual.cpu(), "err": T.tdvp_error.cpu(), "V": V.cpu(), "entropy": info["entropy"].cpu(), "q_eager": q_eager, "q_lazy": q_lazy,
+                "upd_lazy": upd2.cpu()}, args.out)
     print("rank 0 wrote", args.out, "P", vs.numParameters, "world", world, flush=True)
 if world > 1:
     dist.barrier(); dist.destroy_process_group()
