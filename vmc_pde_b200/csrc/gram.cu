@@ -20,6 +20,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstdlib>
 #include <vector>
 #include "common.cuh"
 
@@ -44,6 +45,7 @@ struct GramArgs {
   int tiles_n;    // GEMM: tile cols (N / 128)
   int Pp;         // leading dimension of the outputs
   int full;       // 0: upper-triangular tile pairs of X^T X ; 1: all tiles of X^T Y (second tensor map)
+  int super;      // supertile edge of the SYRK enumeration (tiles)
   double alpha, beta;  // out = alpha * acc + beta * out
   long long n;    // contraction length (samples)
 };
@@ -92,20 +94,36 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
                : "d"(a), "d"(b));
 }
 
-// work item -> (matrix, tile row ti <= tile col tj); matrices innermost so the weighted variants of one
-// tile pair run side by side and share both panels in L2
+// work item -> (matrix, tile row ti <= tile col tj).  Matrices innermost, so the weighted variants of one tile pair run
+// side by side and share both panels in L2; tile pairs are enumerated supertile by supertile (G x G tile blocks, G chosen
+// so that one supertile x n_mats ~ one wave of CTAs): the CTAs of a wave then stream 2 G column panels instead of
+// G^2 + 1, which keeps the panel window of a wave inside the 126 MB L2 even when the CTAs drift apart in the sample index.
 __device__ __forceinline__ void decode_item(long long item, const GramArgs& a, int& mat, int& ti, int& tj) {
   const int n_mats = a.n_mats, tiles = a.tiles;
   mat = (int)(item % n_mats);
   long long p = item / n_mats;
   if (a.full) { ti = (int)(p / a.tiles_n); tj = (int)(p % a.tiles_n); return; }
-  // row-major enumeration of the upper triangle: row ti has (tiles - ti) entries
-  int r = 0;
-  long long rem = p;
-  // closed form would need a sqrt; tiles <= 512 so a short loop is fine
-  while (rem >= (long long)(tiles - r)) { rem -= (tiles - r); ++r; }
-  ti = r;
-  tj = r + (int)rem;
+  const int G = a.super;
+  const int ST = (tiles + G - 1) / G;
+  for (int SI = 0; SI < ST; ++SI) {
+    const int r0 = SI * G, rn = min(G, tiles - r0);
+    long long cnt = (long long)rn * (rn + 1) / 2;   // diagonal supertile: its upper triangle, row by row
+    if (p < cnt) {
+      int r = 0;
+      while (p >= (long long)(rn - r)) { p -= (rn - r); ++r; }
+      ti = r0 + r;
+      tj = r0 + r + (int)p;
+      return;
+    }
+    p -= cnt;
+    for (int SJ = SI + 1; SJ < ST; ++SJ) {
+      const int c0 = SJ * G, cn = min(G, tiles - c0);
+      cnt = (long long)rn * cn;
+      if (p < cnt) { ti = r0 + (int)(p / cn); tj = c0 + (int)(p % cn); return; }
+      p -= cnt;
+    }
+  }
+  ti = tj = 0;  // not reached: item < n_items
 }
 
 __global__ void __launch_bounds__(kGramThreads, 1)
@@ -314,6 +332,9 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_gram(const double* 
   const long long n_items = (long long)n_mats * a.tiles * (a.tiles + 1) / 2;
   int grid = num_sms();
   if (n_items < grid) grid = (int)n_items;
+  a.super = 1;
+  while ((a.super + 1) * (a.super + 1) * n_mats <= grid) ++a.super;
+  if (const char* e_ = getenv("VMCPDE_GRAM_SUPERTILE")) a.super = atoi(e_) > 0 ? atoi(e_) : a.super;
   gram_kernel<<<grid, kGramThreads, smem, (cudaStream_t)stream>>>(map, map, a);
   VMC_LAUNCH_CHECK("gram_kernel");
   return 0;
@@ -333,6 +354,7 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_gemm_tn(const doubl
   if (K == 0) return 0;
   GramArgs a{};
   a.S[0] = Out; a.w[0] = nullptr; a.n_mats = 1; a.tiles = M / 128; a.tiles_n = N / 128; a.Pp = (int)ldo; a.n = K; a.full = 1;
+  a.super = 1;
   a.alpha = alpha; a.beta = beta;
   CUtensorMap mx, my;
   if (int rc = make_panel_tensor_map(&mx, X, K, ldx, M)) return rc;
