@@ -247,6 +247,41 @@ def test_driver_loop_like_main_py():
     assert abs(vs.integrate(g) - 1.0) < 2e-3       # the flow density stays normalised along the evolution
 
 
+def test_phase_space_evolution_follows_the_exact_moment_equations():
+    """main.py mode 'harmonicOsc_diff' with one oscillator: a damped, thermally driven harmonic oscillator in (x, p).
+    Drift is linear and diffusion constant, so the exact density stays Gaussian and its moments obey
+    m' = A m,  C' = A C + C A^T + 2 D  with A = [[0, 1/m], [-m w^2, -gamma]], D = diag(0, m gamma T)
+    (evolutionEq.py:71-76,107-119).  The TDVP-evolved flow density must follow them (evolved density moments are part of
+    the parity contract; the reference's stored trajectories show the same curves)."""
+    from vmc_pde_b200 import tdvp, stepper
+    smp, vs, eq, spec = build(2, 4, 1, "different_add", "Gauss", "advection_hamiltonian_wDiss", np.array([1.0, 0.0]))
+    m_, w_, T_, g_ = 1.0, 1.0, 10.0, 1.0
+    A = np.array([[0.0, 1.0 / m_], [-m_ * w_ ** 2, -g_]]); D = np.diag([0.0, m_ * g_ * T_])
+    mean, cov, t = np.array([1.0, 0.0]), np.eye(2), 0.0
+    st = stepper.FixedStepper(timeStep=4e-3, mode='Heun', maxStep=4e-3, increase_fac=1.0)
+    tdvpEq = tdvp.TDVP()
+    for k in range(50):
+        dp, dt, info = st.step(0, tdvpEq, vs.get_parameters(), evolutionEq=eq, psi=vs, nSamplesTDVP=20000, nSamplesObs=20000,
+                               normFunction=norm_fun, timings=None, integrals=False)
+        vs.set_parameters(dp)
+        # exact moments, RK4 on the same time grid
+        def rhs(mc):
+            mm, cc = mc
+            return A @ mm, A @ cc + cc @ A.T + 2 * D
+        k1 = rhs((mean, cov)); k2 = rhs((mean + 0.5 * dt * k1[0], cov + 0.5 * dt * k1[1]))
+        k3 = rhs((mean + 0.5 * dt * k2[0], cov + 0.5 * dt * k2[1])); k4 = rhs((mean + dt * k3[0], cov + dt * k3[1]))
+        mean = mean + dt / 6 * (k1[0] + 2 * k2[0] + 2 * k3[0] + k4[0]); cov = cov + dt / 6 * (k1[1] + 2 * k2[1] + 2 * k3[1] + k4[1])
+        t += dt
+    # info describes the state BEFORE the last update's second stage; evaluate the final state once more
+    _, info = tdvpEq(vs.get_parameters(), 0.0, psi=vs, evolutionEq=eq, nSamplesTDVP=40000, nSamplesObs=40000, timings=None)
+    x1, cv = info["x1"].cpu().numpy(), info["covar"].cpu().numpy()
+    assert abs(t - 0.2) < 1e-12 and cov[1, 1] > 3.5                       # the momentum variance grew from 1 to ~4
+    assert np.abs(x1 - mean).max() < 0.03
+    assert np.abs(cv - cov).max() < 0.04 * np.abs(cov).max()
+    # E_loc lacks the additive constant gamma (SURVEY A.6), which enters the denominator of tdvp_error: only its range holds
+    assert 0 <= float(tdvpEq.tdvp_error) < 1
+
+
 def test_full_size_properties_c3():
     """BASELINE configs[2] sizes (d=6, P=8187, N=2^18): properties that do not need the oracle at this size --
     symmetric PSD Gram, S theta_dot = F on the retained spectrum, TDVP error in [0,1), Gram trace equals the sum of
