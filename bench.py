@@ -219,10 +219,25 @@ def run_ours(args):
     barrier()
     ms_lazy = tl0.elapsed_time(tl1) / 2
     T.computeSExp = True
+    # second variant: the shifted-Cholesky solve (north-star item 4 allows "diagonal shift ... blocked Cholesky"): no
+    # eigendecomposition, hence no SNR Gram either; the serial fraction of the multi-GPU step all but disappears
+    from vmc_pde_b200 import tdvp as _tdvp
+    Tc = _tdvp.TDVP(diagonalShift=1e-4, solver="cholesky")
+    st.step(0, Tc, vs.get_parameters(), **rhs)
+    barrier()
+    tc0 = torch.cuda.Event(enable_timing=True); tc1 = torch.cuda.Event(enable_timing=True)
+    tc0.record()
+    for _ in range(2):
+        y, _, _ = st.step(0, Tc, vs.get_parameters(), **rhs)
+        vs.set_parameters(y)
+    tc1.record()
+    barrier()
+    ms_chol = tc0.elapsed_time(tc1) / 2
+    del Tc
     if world > 1:
-        t = torch.tensor([ms, ms_e2e, ms_lazy], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms, ms_e2e, ms_lazy, ms_chol], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e, ms_lazy = float(t[0]), float(t[1]), float(t[2])
+        ms, ms_e2e, ms_lazy, ms_chol = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -253,9 +268,11 @@ def run_ours(args):
                      "share_of_step": sum(gram_ms) / ms if gram_ms else None},
         "stages_ms_per_rhs": {"gram": sum(gram_ms) / max(len(eigh_ms), 1), "eigh": sum(eigh_ms) / max(len(eigh_ms), 1),
                               "everything_else": (ms - sum(gram_ms) - sum(eigh_ms)) / max(len(eigh_ms), 1)},
-        "variants": {"lazy_SExp_steps_per_s": 1e3 / ms_lazy,
+        "variants": {"lazy_SExp_steps_per_s": 1e3 / ms_lazy, "cholesky_shift1e-4_steps_per_s": 1e3 / ms_chol,
                      "note": "TDVP(computeSExp='lazy'): SExp kept as a matrix-free operator on the resident O (2 Grams per RHS "
-                             "instead of 3); not the headline -- the reference forms SExp every call"},
+                             "instead of 3); cholesky: TDVP(diagonalShift=1e-4, solver='cholesky') replaces the eigen-solve by the "
+                             "tensor-core blocked Cholesky (S0 and SExp Grams only).  Neither is the headline -- the reference forms "
+                             "SExp every call and regularises through the eigendecomposition"},
         "last_entropy": ent,
     }
     # CPU arm: rank 0 at N=1 only (under torchrun the host threads are pinned to 1 per rank; see --impl reference)

@@ -286,7 +286,7 @@ def test_solve_tail_and_cholesky_against_oracle(L):
         big = np.abs(T.ev / T.ev[-1]) > 1e-8
         assert np.abs(snr[big] / T.snr[big] - 1).max() < 1e-6 and relerr(rhoVar[big], T.rhoVar[big]) < 1e-9
         assert np.array_equal(invEv == 0, T.invEv == 0)
-    for n in (5, 64, 65, 300, 1000):
+    for n in (5, 64, 65, 300, 1000, 1281, 2053):   # n >= 256 with a padded ld takes the tensor-core (upper-form) path
         ld = L.vmcpde_padded_params(n); A = rng.normal(size=(n + 50, n)); Sn = A.T @ A / n + 1e-3 * np.eye(n); Fn = rng.normal(size=n)
         S = torch.zeros(ld, ld, device=dev(), dtype=f64); S[:n, :n] = torch.tensor(Sn, device=dev()); F = torch.tensor(Fn, device=dev())
         x = torch.zeros(n, device=dev(), dtype=f64); info = torch.zeros(1, device=dev(), dtype=torch.int32)

@@ -340,6 +340,32 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_gram(const double* 
   return 0;
 }
 
+// Upper-triangular tiles of Out = alpha * X^T X + beta * Out (X [K x M] row-major, M multiple of 128, K of 16): the SYRK
+// form of the pipeline with a scale, used by the blocked Cholesky's trailing update.
+extern "C" __attribute__((visibility("default"))) int vmcpde_syrk_tn(const double* X, int64_t ldx, double* Out, int64_t ldo, int32_t M, int64_t K,
+                                                                      double alpha, double beta, vmcpde_stream stream) {
+  using namespace vmc;
+  VMC_REQUIRE(X && Out, "vmcpde_syrk_tn: null pointer");
+  VMC_REQUIRE(M > 0 && M % 128 == 0 && K >= 0 && K % kKC == 0, "vmcpde_syrk_tn: M multiple of 128 and K of 16 required");
+  VMC_REQUIRE(ldx >= M && ldo >= M && ldx % 2 == 0 && ldo % 2 == 0 && ldo <= 0x7fffffff, "vmcpde_syrk_tn: bad leading dimensions");
+  if (K == 0) return 0;
+  GramArgs a{};
+  a.S[0] = Out; a.w[0] = nullptr; a.n_mats = 1; a.tiles = M / 128; a.tiles_n = M / 128; a.Pp = (int)ldo; a.n = K; a.full = 0;
+  a.alpha = alpha; a.beta = beta;
+  CUtensorMap mx;
+  if (int rc = make_panel_tensor_map(&mx, X, K, ldx, M)) return rc;
+  const size_t smem = gram_smem_bytes();
+  VMC_CUDA_CHECK(cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long n_items = (long long)a.tiles * (a.tiles + 1) / 2;
+  int grid = num_sms();
+  if (n_items < grid) grid = (int)n_items;
+  a.super = 1;
+  while ((a.super + 1) * (a.super + 1) <= grid) ++a.super;
+  gram_kernel<<<grid, kGramThreads, smem, (cudaStream_t)stream>>>(mx, mx, a);
+  VMC_LAUNCH_CHECK("gram_kernel(syrk_tn)");
+  return 0;
+}
+
 // General FP64 tensor-core product on the same pipeline: Out[M x N] = alpha * X^T Y + beta * Out with
 // X [K x M] (ldx), Y [K x N] (ldy) row-major, i.e. both operands contiguous along the output index
 // (the layout every product of the solve stage is arranged to have).  M, N multiples of 128, K of 16.

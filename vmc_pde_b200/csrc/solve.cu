@@ -6,10 +6,13 @@
 //  * vmcpde_chol_solve: blocked Cholesky fast path for a shifted (positive definite) S
 //    (north-star item 4; admissible only with diagonalShift > 0).
 #include <cstdint>
+#include <cstdlib>
 #include "common.cuh"
 
 extern "C" int vmcpde_gemm_tn(const double* X, int64_t ldx, const double* Y, int64_t ldy, double* Out, int64_t ldo,
                               int32_t M, int32_t N, int64_t K, double alpha, double beta, vmcpde_stream stream);
+extern "C" int vmcpde_syrk_tn(const double* X, int64_t ldx, double* Out, int64_t ldo, int32_t M, int64_t K, double alpha,
+                              double beta, vmcpde_stream stream);
 
 namespace vmc {
 
@@ -306,6 +309,148 @@ __global__ void __launch_bounds__(1024) chol_substitute_kernel(const double* __r
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tensor-core blocked Cholesky (upper form A = U^T U, nb = 128) for padded matrices (ld % 128 == 0).  Per panel:
+//   potrf128_kernel   U11 of the 128 x 128 diagonal block (one CTA, shared memory);
+//   trsm128_kernel    U12 = U11^-T A12 in place, one thread per column of A12 (coalesced rows, U11 broadcast from
+//                     shared memory, 32 right-hand-side entries in registers at a time);
+//   vmcpde_syrk_tn    A22 -= U12^T U12 on the upper-triangular tiles (DMMA pipeline of the Gram kernel).
+// U lives in the upper triangle; the lower triangle is never read.
+constexpr int kCb = 128;
+
+__global__ void __launch_bounds__(256) potrf128_kernel(double* __restrict__ A, int ld, int j0, int n, int* info) {
+  extern __shared__ double sm[];            // U [128][129]
+  double* U = sm;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  for (int idx = tid; idx < kCb * kCb; idx += 256) {
+    const int r = idx >> 7, c = idx & 127;
+    double v = (c >= r) ? A[(size_t)(j0 + r) * ld + j0 + c] : 0.0;
+    if (j0 + r >= n || j0 + c >= n) v = (r == c) ? 1.0 : 0.0;   // identity in the padding
+    U[r * (kCb + 1) + c] = v;
+  }
+  __syncthreads();
+  for (int k = 0; k < kCb; ++k) {
+    if (tid == 0) {
+      const double p = U[k * (kCb + 1) + k];
+      if (!(p > 0.0)) { if (*info == 0) *info = j0 + k + 1; U[k * (kCb + 1) + k] = 1.0; } else U[k * (kCb + 1) + k] = sqrt(p);
+    }
+    __syncthreads();
+    const double d = U[k * (kCb + 1) + k];
+    if (tid > k && tid < kCb) U[k * (kCb + 1) + tid] /= d;
+    __syncthreads();
+    // trailing rows r > k, columns c >= r (16 x 16 thread grid strides over the square; the lower part is skipped)
+    for (int r = k + 1 + ty; r < kCb; r += 16) {
+      const double ukr = U[k * (kCb + 1) + r];
+      for (int c = k + 1 + tx; c < kCb; c += 16)
+        if (c >= r) U[r * (kCb + 1) + c] = fma(-ukr, U[k * (kCb + 1) + c], U[r * (kCb + 1) + c]);
+    }
+    __syncthreads();
+  }
+  for (int idx = tid; idx < kCb * kCb; idx += 256) {
+    const int r = idx >> 7, c = idx & 127;
+    if (j0 + r < n && j0 + c < n && c >= r) A[(size_t)(j0 + r) * ld + j0 + c] = U[r * (kCb + 1) + c];
+  }
+}
+
+// A12 (128 rows j0.., m columns from j1) <- U11^-T A12: forward substitution down each column
+__global__ void __launch_bounds__(128) trsm128_kernel(double* __restrict__ A, int ld, int j0, int m) {
+  extern __shared__ double sm[];            // U11 [128][129]
+  double* U = sm;
+  for (int idx = threadIdx.x; idx < kCb * kCb; idx += 128) {
+    const int r = idx >> 7, c = idx & 127;
+    U[r * (kCb + 1) + c] = (c >= r) ? A[(size_t)(j0 + r) * ld + j0 + c] : 0.0;
+  }
+  __syncthreads();
+  const int col = blockIdx.x * 128 + threadIdx.x;
+  if (col >= m) return;
+  double* a = A + (size_t)j0 * ld + j0 + kCb + col;   // a[k * ld] = A12[k][col]
+  for (int kc = 0; kc < kCb; kc += 32) {
+    double y[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) y[k] = a[(size_t)(kc + k) * ld];
+    for (int q = 0; q < kc; ++q) {            // contributions of the finished chunks
+      const double yq = a[(size_t)q * ld];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) y[k] = fma(-U[q * (kCb + 1) + kc + k], yq, y[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {            // inside the chunk
+      y[k] /= U[(kc + k) * (kCb + 1) + kc + k];
+#pragma unroll
+      for (int k2 = k + 1; k2 < 32; ++k2) y[k2] = fma(-U[(kc + k) * (kCb + 1) + kc + k2], y[k], y[k2]);
+    }
+#pragma unroll
+    for (int k = 0; k < 32; ++k) a[(size_t)(kc + k) * ld] = y[k];
+  }
+}
+
+// U^T y = b, then U x = y (U upper, rows contiguous): one CTA; every 128 x 128 diagonal block and the matching piece of the
+// right-hand side are solved in shared memory, the off-diagonal updates stream U with all threads.
+__global__ void __launch_bounds__(1024) chol_upper_substitute_kernel(const double* __restrict__ U, int ld, int n,
+                                                                     const double* __restrict__ b, double* __restrict__ x) {
+  extern __shared__ double sm[];            // Ud [128][129], blk [128]
+  double* Ud = sm;
+  double* blk = sm + kCb * (kCb + 1);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < n; i += blockDim.x) x[i] = b[i];
+  __syncthreads();
+  auto load_block = [&](int j0, int nbk) {
+    for (int idx = tid; idx < kCb * kCb; idx += 1024) {
+      const int r = idx >> 7, c = idx & 127;
+      Ud[r * (kCb + 1) + c] = (r < nbk && c < nbk && c >= r) ? U[(size_t)(j0 + r) * ld + j0 + c] : (r == c ? 1.0 : 0.0);
+    }
+    if (tid < kCb) blk[tid] = tid < nbk ? x[j0 + tid] : 0.0;
+  };
+  // forward: U^T y = b (column sweep: once y_r is known, the later entries lose U[r][c] y_r)
+  for (int j0 = 0; j0 < n; j0 += kCb) {
+    const int nbk = min(kCb, n - j0);
+    load_block(j0, nbk);
+    __syncthreads();
+    if (warp == 0) {
+      for (int r = 0; r < nbk; ++r) {
+        const double yr = blk[r] / Ud[r * (kCb + 1) + r];
+        __syncwarp();
+        if (lane == 0) blk[r] = yr;
+        for (int c = r + 1 + lane; c < nbk; c += 32) blk[c] = fma(-Ud[r * (kCb + 1) + c], yr, blk[c]);
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    if (tid < nbk) x[j0 + tid] = blk[tid];
+    for (int c = j0 + nbk + tid; c < n; c += blockDim.x) {
+      double sacc = 0.0;
+      for (int r = 0; r < nbk; ++r) sacc = fma(U[(size_t)(j0 + r) * ld + c], blk[r], sacc);
+      x[c] -= sacc;
+    }
+    __syncthreads();
+  }
+  // backward: U x = y (row sweep from the bottom)
+  for (int j0 = ((n - 1) / kCb) * kCb; j0 >= 0; j0 -= kCb) {
+    const int nbk = min(kCb, n - j0);
+    load_block(j0, nbk);
+    __syncthreads();
+    for (int r = warp; r < nbk; r += 32) {    // off-block part of row r: warp per row
+      double sacc = 0.0;
+      for (int c = j0 + nbk + lane; c < n; c += 32) sacc = fma(U[(size_t)(j0 + r) * ld + c], x[c], sacc);
+      sacc = wsum(sacc);
+      if (lane == 0) blk[r] -= sacc;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      for (int r = nbk - 1; r >= 0; --r) {
+        double sacc = 0.0;
+        for (int c = r + 1 + lane; c < nbk; c += 32) sacc = fma(Ud[r * (kCb + 1) + c], blk[c], sacc);
+        sacc = wsum(sacc);
+        if (lane == 0) blk[r] = (blk[r] - sacc) / Ud[r * (kCb + 1) + r];
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    if (tid < nbk) x[j0 + tid] = blk[tid];
+    __syncthreads();
+  }
+}
+
 static size_t al(size_t x) { return (x + 255) / 256 * 256; }
 
 }  // namespace vmc
@@ -396,6 +541,26 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_chol_solve(double* 
   VMC_REQUIRE(S && F && x && info, "vmcpde_chol_solve: null pointer");
   VMC_REQUIRE(n >= 1 && ld >= n, "vmcpde_chol_solve: bad dimensions");
   cudaStream_t s = (cudaStream_t)stream;
+  if (ld % 128 == 0 && n >= 256 && ld >= (n + 127) / 128 * 128 && !getenv("VMCPDE_CHOL_LEGACY")) {
+    // tensor-core path (S is an ld x ld buffer, as every caller of this package allocates it; its lower triangle is scratch)
+    const int np = (n + 127) / 128 * 128;
+    const size_t psm = (size_t)kCb * (kCb + 1) * 8;
+    VMC_CUDA_CHECK(cudaFuncSetAttribute(potrf128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+    VMC_CUDA_CHECK(cudaFuncSetAttribute(trsm128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+    VMC_CUDA_CHECK(cudaFuncSetAttribute(chol_upper_substitute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(psm + kCb * 8)));
+    for (int j0 = 0; j0 < np; j0 += kCb) {
+      const int j1 = j0 + kCb, m = np - j1;
+      potrf128_kernel<<<1, 256, psm, s>>>(S, ld, j0, n, info);
+      if (m > 0) {
+        trsm128_kernel<<<(m + 127) / 128, 128, psm, s>>>(S, ld, j0, m);
+        double* A12 = S + (size_t)j0 * ld + j1;
+        if (int rc = vmcpde_syrk_tn(A12, ld, S + (size_t)j1 * ld + j1, ld, m, kCb, -1.0, 1.0, stream)) return rc;
+      }
+    }
+    chol_upper_substitute_kernel<<<1, 1024, psm + kCb * 8, s>>>(S, ld, n, F, x);
+    VMC_LAUNCH_CHECK("chol_solve (tensor-core path)");
+    return 0;
+  }
   for (int j0 = 0; j0 < n; j0 += kNb) {
     const int nb = min(kNb, n - j0);
     potrf_diag_kernel<<<1, 256, 0, s>>>(S, ld, j0, nb, info);
