@@ -133,6 +133,7 @@ def run_ours(args):
         vs.set_parameters(y)
         return info
 
+    theta_init = vs.get_parameters().clone()
     host_theta = torch.empty(P, dtype=torch.float64).pin_memory()
     host_theta.copy_(vs.get_parameters().cpu())
     host_out = torch.empty(P + 3, dtype=torch.float64).pin_memory()
@@ -223,6 +224,9 @@ def run_ours(args):
     # eigendecomposition, hence no SNR Gram either; the serial fraction of the multi-GPU step all but disappears
     from vmc_pde_b200 import tdvp as _tdvp
     Tc = _tdvp.TDVP(diagonalShift=1e-4, solver="cholesky")
+    vs.set_parameters(theta_init)      # timing variant: start again from the initial state with a fresh, small step
+    from vmc_pde_b200 import stepper as _stepper
+    st = _stepper.FixedStepper(timeStep=1e-4, mode='Heun', maxStep=1e-2, increase_fac=1.3)
     st.step(0, Tc, vs.get_parameters(), **rhs)
     barrier()
     tc0 = torch.cuda.Event(enable_timing=True); tc1 = torch.cuda.Event(enable_timing=True)

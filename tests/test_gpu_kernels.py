@@ -297,3 +297,11 @@ def test_solve_tail_and_cholesky_against_oracle(L):
     info = torch.zeros(1, device=dev(), dtype=torch.int32); x = torch.zeros(4, device=dev(), dtype=f64)
     _lib.check(L.vmcpde_chol_solve(_lib.ptr(S), 4, 128, _lib.ptr(torch.ones(4, device=dev(), dtype=f64)), _lib.ptr(x), _lib.ptr(info), _lib.stream()))
     assert int(info) == 2
+    # ... while a parameter nothing depends on (exactly zero row and column) just gets a zero update
+    n = 300; ld = L.vmcpde_padded_params(n); A = rng.normal(size=(n + 50, n)); A[:, 17] = 0.0; Sn = A.T @ A / n + 1e-3 * np.diag(np.diag(A.T @ A / n))
+    Fn = rng.normal(size=n); Fn[17] = 0.0
+    S = torch.zeros(ld, ld, device=dev(), dtype=f64); S[:n, :n] = torch.tensor(Sn, device=dev()); F = torch.tensor(Fn, device=dev())
+    x = torch.zeros(n, device=dev(), dtype=f64); info = torch.zeros(1, device=dev(), dtype=torch.int32)
+    _lib.check(L.vmcpde_chol_solve(_lib.ptr(S), n, ld, _lib.ptr(F), _lib.ptr(x), _lib.ptr(info), _lib.stream()))
+    keep = np.arange(n) != 17
+    assert int(info) == 0 and float(x[17]) == 0.0 and relerr(x.cpu().numpy()[keep], np.linalg.solve(Sn[np.ix_(keep, keep)], Fn[keep])) < 1e-10

@@ -6,6 +6,7 @@
 //  * vmcpde_chol_solve: blocked Cholesky fast path for a shifted (positive definite) S
 //    (north-star item 4; admissible only with diagonalShift > 0).
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include "common.cuh"
 
@@ -147,6 +148,14 @@ __global__ void __launch_bounds__(1024) solve_scalars_kernel(const double* __res
     scalars[0] = sqrt(a) / sqrt(b);
     scalars[1] = 1.0 + (c - 2.0 * d) / meanE2;
   }
+}
+
+// A parameter no sample depends on gives an exactly zero row and column of the Gram, and the multiplicative shift of
+// tdvp.py:50-51 adds shift * 0 to its diagonal.  Such a diagonal entry is set to 1 before factorising, so the parameter
+// gets the update F_i / 1 = 0 -- what the eigen-solve assigns to a null direction -- instead of failing the factorisation.
+__global__ void zero_diag_to_one_kernel(double* __restrict__ A, int ld, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && A[(size_t)i * ld + i] == 0.0) A[(size_t)i * ld + i] = 1.0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -541,6 +550,7 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_chol_solve(double* 
   VMC_REQUIRE(S && F && x && info, "vmcpde_chol_solve: null pointer");
   VMC_REQUIRE(n >= 1 && ld >= n, "vmcpde_chol_solve: bad dimensions");
   cudaStream_t s = (cudaStream_t)stream;
+  zero_diag_to_one_kernel<<<(n + 255) / 256, 256, 0, s>>>(S, ld, n);
   if (ld % 128 == 0 && n >= 256 && ld >= (n + 127) / 128 * 128 && !getenv("VMCPDE_CHOL_LEGACY")) {
     // tensor-core path (S is an ld x ld buffer, as every caller of this package allocates it; its lower triangle is scratch)
     const int np = (n + 127) / 128 * 128;
@@ -548,16 +558,28 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_chol_solve(double* 
     VMC_CUDA_CHECK(cudaFuncSetAttribute(potrf128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
     VMC_CUDA_CHECK(cudaFuncSetAttribute(trsm128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
     VMC_CUDA_CHECK(cudaFuncSetAttribute(chol_upper_substitute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(psm + kCb * 8)));
+    const bool timing = getenv("VMCPDE_CHOL_TIMING") != nullptr;   // debugging aid: synchronises
+    float t_potrf = 0.f, t_trsm = 0.f, t_syrk = 0.f, t_sub = 0.f;
+    cudaEvent_t ev[2];
+    if (timing) { cudaEventCreate(&ev[0]); cudaEventCreate(&ev[1]); }
+    auto tic = [&]() { if (timing) cudaEventRecord(ev[0], s); };
+    auto toc = [&](float& acc) { if (timing) { cudaEventRecord(ev[1], s); cudaEventSynchronize(ev[1]); float ms; cudaEventElapsedTime(&ms, ev[0], ev[1]); acc += ms; } };
     for (int j0 = 0; j0 < np; j0 += kCb) {
       const int j1 = j0 + kCb, m = np - j1;
-      potrf128_kernel<<<1, 256, psm, s>>>(S, ld, j0, n, info);
+      tic(); potrf128_kernel<<<1, 256, psm, s>>>(S, ld, j0, n, info); toc(t_potrf);
       if (m > 0) {
-        trsm128_kernel<<<(m + 127) / 128, 128, psm, s>>>(S, ld, j0, m);
+        tic(); trsm128_kernel<<<(m + 127) / 128, 128, psm, s>>>(S, ld, j0, m); toc(t_trsm);
         double* A12 = S + (size_t)j0 * ld + j1;
+        tic();
         if (int rc = vmcpde_syrk_tn(A12, ld, S + (size_t)j1 * ld + j1, ld, m, kCb, -1.0, 1.0, stream)) return rc;
+        toc(t_syrk);
       }
     }
-    chol_upper_substitute_kernel<<<1, 1024, psm + kCb * 8, s>>>(S, ld, n, F, x);
+    tic(); chol_upper_substitute_kernel<<<1, 1024, psm + kCb * 8, s>>>(S, ld, n, F, x); toc(t_sub);
+    if (timing) {
+      fprintf(stderr, "[vmcpde_chol_solve n=%d] potrf %.2f ms, trsm %.2f ms, syrk %.2f ms, substitution %.2f ms\n", n, t_potrf, t_trsm, t_syrk, t_sub);
+      cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+    }
     VMC_LAUNCH_CHECK("chol_solve (tensor-core path)");
     return 0;
   }
