@@ -328,37 +328,68 @@ __global__ void __launch_bounds__(1024) chol_substitute_kernel(const double* __r
 constexpr int kCb = 128;
 
 __global__ void __launch_bounds__(256) potrf128_kernel(double* __restrict__ A, int ld, int j0, int n, int* info) {
-  extern __shared__ double sm[];            // U [128][129]
-  double* U = sm;
+  // Register-tiled right-looking factorisation: thread (ty, tx) of a 16 x 16 grid owns the entries (ty + 16 i, tx + 16 j)
+  // of the block (cyclic, so the shrinking trailing part stays balanced); per step the scaled pivot row goes through
+  // shared memory and every thread applies the rank-1 update to its 8 x 8 registers.
+  __shared__ double rowk[kCb];
+  __shared__ double piv;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  for (int idx = tid; idx < kCb * kCb; idx += 256) {
-    const int r = idx >> 7, c = idx & 127;
-    double v = (c >= r) ? A[(size_t)(j0 + r) * ld + j0 + c] : 0.0;
-    if (j0 + r >= n || j0 + c >= n) v = (r == c) ? 1.0 : 0.0;   // identity in the padding
-    U[r * (kCb + 1) + c] = v;
-  }
-  __syncthreads();
+  double u[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int r = ty + 16 * i, c = tx + 16 * j;
+      double v = (c >= r && j0 + r < n && j0 + c < n) ? A[(size_t)(j0 + r) * ld + j0 + c] : 0.0;
+      if ((j0 + r >= n || j0 + c >= n) && r == c) v = 1.0;   // identity in the padding
+      u[i][j] = v;
+    }
   for (int k = 0; k < kCb; ++k) {
-    if (tid == 0) {
-      const double p = U[k * (kCb + 1) + k];
-      if (!(p > 0.0)) { if (*info == 0) *info = j0 + k + 1; U[k * (kCb + 1) + k] = 1.0; } else U[k * (kCb + 1) + k] = sqrt(p);
+    const int ki = k >> 4, kt = k & 15;   // row k lives in register row ki of the threads with ty == kt (same for columns)
+    if (ty == kt && tx == kt) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i == ki) piv = u[i][i];
     }
     __syncthreads();
-    const double d = U[k * (kCb + 1) + k];
-    if (tid > k && tid < kCb) U[k * (kCb + 1) + tid] /= d;
-    __syncthreads();
-    // trailing rows r > k, columns c >= r (16 x 16 thread grid strides over the square; the lower part is skipped)
-    for (int r = k + 1 + ty; r < kCb; r += 16) {
-      const double ukr = U[k * (kCb + 1) + r];
-      for (int c = k + 1 + tx; c < kCb; c += 16)
-        if (c >= r) U[r * (kCb + 1) + c] = fma(-ukr, U[k * (kCb + 1) + c], U[r * (kCb + 1) + c]);
+    const double p = piv;
+    double d = 1.0;
+    if (!(p > 0.0)) { if (tid == 0 && *info == 0) *info = j0 + k + 1; } else d = sqrt(p);
+    const double dinv = 1.0 / d;
+    if (ty == kt) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i == ki) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int c = tx + 16 * j;
+            if (c > k) u[i][j] *= dinv; else if (c == k) u[i][j] = d;
+            rowk[c] = u[i][j];
+          }
+        }
     }
     __syncthreads();
+    double rk[8], ck[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) rk[i] = rowk[ty + 16 * i];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ck[j] = rowk[tx + 16 * j];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int r = ty + 16 * i, c = tx + 16 * j;
+        if (r > k && c >= r) u[i][j] = fma(-rk[i], ck[j], u[i][j]);
+      }
+    // the next step's pivot write happens before its barrier; rowk is rewritten only after that barrier
   }
-  for (int idx = tid; idx < kCb * kCb; idx += 256) {
-    const int r = idx >> 7, c = idx & 127;
-    if (j0 + r < n && j0 + c < n && c >= r) A[(size_t)(j0 + r) * ld + j0 + c] = U[r * (kCb + 1) + c];
-  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int r = ty + 16 * i, c = tx + 16 * j;
+      if (j0 + r < n && j0 + c < n && c >= r) A[(size_t)(j0 + r) * ld + j0 + c] = u[i][j];
+    }
 }
 
 // A12 (128 rows j0.., m columns from j1) <- U11^-T A12: forward substitution down each column
@@ -393,71 +424,85 @@ __global__ void __launch_bounds__(128) trsm128_kernel(double* __restrict__ A, in
   }
 }
 
-// U^T y = b, then U x = y (U upper, rows contiguous): one CTA; every 128 x 128 diagonal block and the matching piece of the
-// right-hand side are solved in shared memory, the off-diagonal updates stream U with all threads.
-__global__ void __launch_bounds__(1024) chol_upper_substitute_kernel(const double* __restrict__ U, int ld, int n,
-                                                                     const double* __restrict__ b, double* __restrict__ x) {
+// Substitution U^T y = b, U x = y (U upper, rows contiguous), block by block: the 128 x 128 diagonal solves run in one CTA
+// out of shared memory, the off-diagonal parts are streamed by the whole GPU.
+// forward diagonal block: x[j0..] <- U11^-T x[j0..]
+__global__ void __launch_bounds__(128) chol_diag_forward_kernel(const double* __restrict__ U, int ld, int n, int j0, double* __restrict__ x) {
   extern __shared__ double sm[];            // Ud [128][129], blk [128]
   double* Ud = sm;
   double* blk = sm + kCb * (kCb + 1);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < n; i += blockDim.x) x[i] = b[i];
+  const int nbk = min(kCb, n - j0);
+  for (int idx = tid; idx < kCb * kCb; idx += 128) {
+    const int r = idx >> 7, c = idx & 127;
+    Ud[r * (kCb + 1) + c] = (r < nbk && c < nbk && c >= r) ? U[(size_t)(j0 + r) * ld + j0 + c] : (r == c ? 1.0 : 0.0);
+  }
+  blk[tid] = tid < nbk ? x[j0 + tid] : 0.0;
   __syncthreads();
-  auto load_block = [&](int j0, int nbk) {
-    for (int idx = tid; idx < kCb * kCb; idx += 1024) {
-      const int r = idx >> 7, c = idx & 127;
-      Ud[r * (kCb + 1) + c] = (r < nbk && c < nbk && c >= r) ? U[(size_t)(j0 + r) * ld + j0 + c] : (r == c ? 1.0 : 0.0);
+  if (warp == 0) {
+    for (int r = 0; r < nbk; ++r) {
+      const double yr = blk[r] / Ud[r * (kCb + 1) + r];
+      __syncwarp();
+      if (lane == 0) blk[r] = yr;
+      for (int c = r + 1 + lane; c < nbk; c += 32) blk[c] = fma(-Ud[r * (kCb + 1) + c], yr, blk[c]);
+      __syncwarp();
     }
-    if (tid < kCb) blk[tid] = tid < nbk ? x[j0 + tid] : 0.0;
-  };
-  // forward: U^T y = b (column sweep: once y_r is known, the later entries lose U[r][c] y_r)
-  for (int j0 = 0; j0 < n; j0 += kCb) {
-    const int nbk = min(kCb, n - j0);
-    load_block(j0, nbk);
-    __syncthreads();
-    if (warp == 0) {
-      for (int r = 0; r < nbk; ++r) {
-        const double yr = blk[r] / Ud[r * (kCb + 1) + r];
-        __syncwarp();
-        if (lane == 0) blk[r] = yr;
-        for (int c = r + 1 + lane; c < nbk; c += 32) blk[c] = fma(-Ud[r * (kCb + 1) + c], yr, blk[c]);
-        __syncwarp();
-      }
-    }
-    __syncthreads();
-    if (tid < nbk) x[j0 + tid] = blk[tid];
-    for (int c = j0 + nbk + tid; c < n; c += blockDim.x) {
-      double sacc = 0.0;
-      for (int r = 0; r < nbk; ++r) sacc = fma(U[(size_t)(j0 + r) * ld + c], blk[r], sacc);
-      x[c] -= sacc;
-    }
-    __syncthreads();
   }
-  // backward: U x = y (row sweep from the bottom)
-  for (int j0 = ((n - 1) / kCb) * kCb; j0 >= 0; j0 -= kCb) {
-    const int nbk = min(kCb, n - j0);
-    load_block(j0, nbk);
-    __syncthreads();
-    for (int r = warp; r < nbk; r += 32) {    // off-block part of row r: warp per row
+  __syncthreads();
+  if (tid < nbk) x[j0 + tid] = blk[tid];
+}
+// forward off-block update: x[c] -= sum_r U[j0 + r][c] y[j0 + r] for c >= j0 + 128
+__global__ void __launch_bounds__(256) chol_offblock_forward_kernel(const double* __restrict__ U, int ld, int n, int j0, double* __restrict__ x) {
+  __shared__ double yb[kCb];
+  if (threadIdx.x < kCb) yb[threadIdx.x] = x[j0 + threadIdx.x];
+  __syncthreads();
+  const int c = j0 + kCb + blockIdx.x * 256 + threadIdx.x;
+  if (c >= n) return;
+  double s0 = 0.0, s1 = 0.0;
+#pragma unroll 8
+  for (int r = 0; r < kCb; r += 2) {
+    s0 = fma(U[(size_t)(j0 + r) * ld + c], yb[r], s0);
+    s1 = fma(U[(size_t)(j0 + r + 1) * ld + c], yb[r + 1], s1);
+  }
+  x[c] -= s0 + s1;
+}
+// backward: x[j0 + r] <- (x[j0 + r] - sum_{c >= j0 + 128} U[j0 + r][c] x[c]) then the diagonal block solve.  The row dots
+// run as one warp per row over 16 CTAs, the block solve in the last-arriving... (kept simple: two kernels)
+__global__ void __launch_bounds__(256) chol_offblock_backward_kernel(const double* __restrict__ U, int ld, int n, int j0, double* __restrict__ x) {
+  const int lane = threadIdx.x & 31, r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int nbk = min(kCb, n - j0);
+  if (r >= nbk) return;
+  const double* row = U + (size_t)(j0 + r) * ld;
+  double s0 = 0.0, s1 = 0.0;
+  int c = j0 + kCb + lane;
+  for (; c + 32 < n; c += 64) { s0 = fma(row[c], x[c], s0); s1 = fma(row[c + 32], x[c + 32], s1); }
+  if (c < n) s0 = fma(row[c], x[c], s0);
+  const double sacc = wsum(s0 + s1);
+  if (lane == 0) x[j0 + r] -= sacc;
+}
+__global__ void __launch_bounds__(128) chol_diag_backward_kernel(const double* __restrict__ U, int ld, int n, int j0, double* __restrict__ x) {
+  extern __shared__ double sm[];
+  double* Ud = sm;
+  double* blk = sm + kCb * (kCb + 1);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nbk = min(kCb, n - j0);
+  for (int idx = tid; idx < kCb * kCb; idx += 128) {
+    const int r = idx >> 7, c = idx & 127;
+    Ud[r * (kCb + 1) + c] = (r < nbk && c < nbk && c >= r) ? U[(size_t)(j0 + r) * ld + j0 + c] : (r == c ? 1.0 : 0.0);
+  }
+  blk[tid] = tid < nbk ? x[j0 + tid] : 0.0;
+  __syncthreads();
+  if (warp == 0) {
+    for (int r = nbk - 1; r >= 0; --r) {
       double sacc = 0.0;
-      for (int c = j0 + nbk + lane; c < n; c += 32) sacc = fma(U[(size_t)(j0 + r) * ld + c], x[c], sacc);
+      for (int c = r + 1 + lane; c < nbk; c += 32) sacc = fma(Ud[r * (kCb + 1) + c], blk[c], sacc);
       sacc = wsum(sacc);
-      if (lane == 0) blk[r] -= sacc;
+      if (lane == 0) blk[r] = (blk[r] - sacc) / Ud[r * (kCb + 1) + r];
+      __syncwarp();
     }
-    __syncthreads();
-    if (warp == 0) {
-      for (int r = nbk - 1; r >= 0; --r) {
-        double sacc = 0.0;
-        for (int c = r + 1 + lane; c < nbk; c += 32) sacc = fma(Ud[r * (kCb + 1) + c], blk[c], sacc);
-        sacc = wsum(sacc);
-        if (lane == 0) blk[r] = (blk[r] - sacc) / Ud[r * (kCb + 1) + r];
-        __syncwarp();
-      }
-    }
-    __syncthreads();
-    if (tid < nbk) x[j0 + tid] = blk[tid];
-    __syncthreads();
   }
+  __syncthreads();
+  if (tid < nbk) x[j0 + tid] = blk[tid];
 }
 
 static size_t al(size_t x) { return (x + 255) / 256 * 256; }
@@ -555,9 +600,9 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_chol_solve(double* 
     // tensor-core path (S is an ld x ld buffer, as every caller of this package allocates it; its lower triangle is scratch)
     const int np = (n + 127) / 128 * 128;
     const size_t psm = (size_t)kCb * (kCb + 1) * 8;
-    VMC_CUDA_CHECK(cudaFuncSetAttribute(potrf128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
     VMC_CUDA_CHECK(cudaFuncSetAttribute(trsm128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
-    VMC_CUDA_CHECK(cudaFuncSetAttribute(chol_upper_substitute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(psm + kCb * 8)));
+    VMC_CUDA_CHECK(cudaFuncSetAttribute(chol_diag_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(psm + kCb * 8)));
+    VMC_CUDA_CHECK(cudaFuncSetAttribute(chol_diag_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(psm + kCb * 8)));
     const bool timing = getenv("VMCPDE_CHOL_TIMING") != nullptr;   // debugging aid: synchronises
     float t_potrf = 0.f, t_trsm = 0.f, t_syrk = 0.f, t_sub = 0.f;
     cudaEvent_t ev[2];
@@ -566,7 +611,7 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_chol_solve(double* 
     auto toc = [&](float& acc) { if (timing) { cudaEventRecord(ev[1], s); cudaEventSynchronize(ev[1]); float ms; cudaEventElapsedTime(&ms, ev[0], ev[1]); acc += ms; } };
     for (int j0 = 0; j0 < np; j0 += kCb) {
       const int j1 = j0 + kCb, m = np - j1;
-      tic(); potrf128_kernel<<<1, 256, psm, s>>>(S, ld, j0, n, info); toc(t_potrf);
+      tic(); potrf128_kernel<<<1, 256, 0, s>>>(S, ld, j0, n, info); toc(t_potrf);
       if (m > 0) {
         tic(); trsm128_kernel<<<(m + 127) / 128, 128, psm, s>>>(S, ld, j0, m); toc(t_trsm);
         double* A12 = S + (size_t)j0 * ld + j1;
@@ -575,7 +620,18 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_chol_solve(double* 
         toc(t_syrk);
       }
     }
-    tic(); chol_upper_substitute_kernel<<<1, 1024, psm + kCb * 8, s>>>(S, ld, n, F, x); toc(t_sub);
+    tic();
+    VMC_CUDA_CHECK(cudaMemcpyAsync(x, F, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
+    for (int j0 = 0; j0 < n; j0 += kCb) {
+      chol_diag_forward_kernel<<<1, 128, psm + kCb * 8, s>>>(S, ld, n, j0, x);
+      const int rest = n - j0 - kCb;
+      if (rest > 0) chol_offblock_forward_kernel<<<(rest + 255) / 256, 256, 0, s>>>(S, ld, n, j0, x);
+    }
+    for (int j0 = ((n - 1) / kCb) * kCb; j0 >= 0; j0 -= kCb) {
+      if (n - j0 - kCb > 0) chol_offblock_backward_kernel<<<kCb / 8, 256, 0, s>>>(S, ld, n, j0, x);
+      chol_diag_backward_kernel<<<1, 128, psm + kCb * 8, s>>>(S, ld, n, j0, x);
+    }
+    toc(t_sub);
     if (timing) {
       fprintf(stderr, "[vmcpde_chol_solve n=%d] potrf %.2f ms, trsm %.2f ms, syrk %.2f ms, substitution %.2f ms\n", n, t_potrf, t_trsm, t_syrk, t_sub);
       cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
