@@ -227,6 +227,14 @@ int vmcpde_ball_points(uint32_t key0, uint32_t key1, int64_t first, int64_t n, i
 /* out[0] += sum_i exp(logp[i]) */
 int vmcpde_sum_exp(const double* logp, int64_t n, double* out, void* ws, vmcpde_stream stream);
 
+/* ---- (6) particle reference dynamics (exact_dyn.py) ----------------------------------------------- */
+/* One step of exact_dyn.integrate (exact_dyn.py:70-84) for n particles (coords [n][d], in place): the 4-stage stochastic
+ * scheme of integrate_single_coord with per-particle keys split(key, n)[i] -> split(., 4) and normal(key, (d,)) noise in
+ * JAX's counter layout.  update: 0 = update_fun_phaseSpace, 1 = update_fun_Diff; field: 0 = _velocity_field_hamiltonian
+ * (uncoupled), 1 = _velocity_field_fluiddynpaper, -1 = none.  eq supplies D, m, omega, lam, T, gamma, t. */
+int vmcpde_particles_step(double* coords, int64_t n, int32_t d, double dt, int32_t update, int32_t field,
+                          const vmcpde_equation* eq, uint32_t key0, uint32_t key1, vmcpde_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -129,3 +129,27 @@ def test_steppers_against_closed_form():
     assert np.allclose(y, 1 - 2e-2)
     y, rdt, ndt = tdvp.adaptive_heun_step(f, np.array([1.0]), 0.1, 1e-6, 1.0, lambda v: float(v @ v))
     assert rdt <= 0.1 and ndt <= 1.0 and abs(y[0] - np.exp(-rdt)) < 1e-4
+
+
+def test_particle_oracle_statistics():
+    """oracle/exact_dyn.py (exact_dyn.py:56-84): one step of the stochastic scheme reproduces drift and noise strength of
+    the phase-space equation to O(dt^2) and Monte-Carlo accuracy, and is a pure function of the key."""
+    from oracle import exact_dyn as ed, threefry as tf
+    p = {"m": 1.0, "omega": 1.0, "lam": 0.0, "T": 10.0, "gamma": 1.0, "t": 0.0, "D": 1.0}
+    rng = np.random.default_rng(0)
+    N, dt = 4000, 1e-2
+    x0 = np.tile(np.array([1.0, 0.5]), (N, 1))
+    key = tf.prng_key(3)
+    x1 = ed.integrate(x0, dt, p, ed.velocity_hamiltonian, ed.update_phase_space, key)
+    assert np.array_equal(x1, ed.integrate(x0, dt, p, ed.velocity_hamiltonian, ed.update_phase_space, key))
+    # mean drift: dx = p dt, dp = (-x - gamma p) dt ; noise only on p.  The scheme weights the four stage noises
+    # (1, 2, 2, 1)/6 with stage steps dt/6, dt/3, dt/3, dt/6: Var[dp] = 2 m gamma T dt (1/6 + 2/3 + 2/3 + 1/6) / ... -> computed below
+    assert abs(x1[:, 0].mean() - (1.0 + 0.5 * dt)) < 5e-4
+    assert abs(x1[:, 1].mean() - (0.5 + (-1.0 - 0.5) * dt)) < 3 * np.sqrt(2 * 10 * dt * 1.5 / N) + 1e-3
+    w = np.array([1, 2, 2, 1]) / 6.0; dts = np.array([dt / 6, dt / 3, dt / 3, dt / 6])
+    var_expected = (dt ** 2) * np.sum(w ** 2 * 2 * p["m"] * p["gamma"] * p["T"] / dts)
+    assert abs(x1[:, 1].var() / var_expected - 1) < 0.1
+    # pure diffusion: isotropic, zero mean
+    y1 = ed.integrate(np.zeros((N, 2)), dt, p, None, ed.update_diffusion, key)
+    vd = (dt ** 2) * np.sum(w ** 2 * 2 / dts)
+    assert abs(y1.mean()) < 4 * np.sqrt(vd / N) and abs(y1.var() / vd - 1) < 0.1

@@ -308,6 +308,14 @@ def ball_points(key, first, n, n_total, d, radius):
     return out
 
 
+def particles_step(coords, dt, update, field, eq, key):
+    """In-place exact_dyn.integrate step on coords [n, d] (update / field: see vmcpde_particles_step)."""
+    _count(1)
+    n, d = coords.shape
+    _lib.check(_lib.load().vmcpde_particles_step(_lib.ptr(coords), int(n), int(d), float(dt), int(update), int(field), C.byref(eq),
+                                                 int(key[0]), int(key[1]), _lib.stream()))
+
+
 def sum_exp(logp_, n, out, ws):
     _count(2)
     _lib.check(_lib.load().vmcpde_sum_exp(_lib.ptr(logp_), int(n), _lib.ptr(out), _lib.ptr(ws), _lib.stream()))

@@ -55,6 +55,7 @@ SIGNATURES = {
     "vmcpde_obs_first": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "vmcpde_obs_central": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "vmcpde_ball_points": (C.c_int, [_u32, _u32, _i64, _i64, _i64, _i32, _dbl, _vp, _vp]),
+    "vmcpde_particles_step": (C.c_int, [_vp, _i64, _i32, _dbl, _i32, _i32, C.POINTER(Equation), _u32, _u32, _vp]),
     "vmcpde_sum_exp": (C.c_int, [_vp, _i64, _vp, _vp, _vp]),
 }
 # filled in as later translation units land (solve / eigh / observables)

@@ -19,7 +19,7 @@ DIMS = (2, 3, 4, 5, 6, 8, 10, 12)
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
-PLAIN = ["capi.cu", "gram.cu", "reduce_kernels.cu", "solve.cu", "eigh.cu", "eigh_blocked.cu", "observables.cu"]
+PLAIN = ["capi.cu", "gram.cu", "reduce_kernels.cu", "solve.cu", "eigh.cu", "eigh_blocked.cu", "observables.cu", "particles.cu"]
 
 
 def _units():
