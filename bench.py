@@ -238,6 +238,24 @@ def run_ours(args):
     barrier()
     ms_chol = tc0.elapsed_time(tc1) / 2
     del Tc
+    adaptive = None
+    if args.adaptive:   # C3 with the adaptive integrator -- one attempt = 5 right-hand sides + the SExp error norm
+        from vmc_pde_b200 import stepper as _stp
+        out_a = {}
+        for mode in (True, "lazy"):
+            vs.set_parameters(theta_init)
+            Ta = _tdvp.TDVP(computeSExp=mode)
+            ah = _stp.AdaptiveHeun(timeStep=1e-4, tol=1e-2, maxStep=1e-2)   # main.py:109-112
+            barrier()
+            ta0 = torch.cuda.Event(enable_timing=True); ta1 = torch.cuda.Event(enable_timing=True)
+            calls0 = _kernels.launches
+            ta0.record()
+            y, dt_used, _ = ah.step(0, Ta, vs.get_parameters(), **rhs)
+            ta1.record()
+            barrier()
+            out_a["eager_SExp" if mode is True else "lazy_SExp"] = {"seconds_per_accepted_step": ta0.elapsed_time(ta1) * 1e-3, "dt": float(dt_used)}
+            del Ta
+        adaptive = out_a
     if world > 1:
         t = torch.tensor([ms, ms_e2e, ms_lazy, ms_chol], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -279,6 +297,8 @@ def run_ours(args):
                              "SExp every call and regularises through the eigendecomposition"},
         "last_entropy": ent,
     }
+    if adaptive is not None:
+        line["variants"]["adaptive_heun"] = adaptive
     # CPU arm: rank 0 at N=1 only (under torchrun the host threads are pinned to 1 per rank; see --impl reference)
     line["cpu_baseline"] = cpu_baseline(bounded_seconds=True) if world == 1 else None
     print(json.dumps(line), flush=True)
@@ -371,6 +391,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--adaptive", action="store_true",
+                    help="also time AdaptiveHeun attempts (5 RHS each, stepper.py:54-66) on the same workload; adds ~30 s")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
