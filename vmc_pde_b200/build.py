@@ -17,8 +17,9 @@ OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libvmcpde.so")
 DIMS = (2, 3, 4, 5, 6, 8, 10, 12)
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+EXTRA = os.environ.get("VMCPDE_NVCC_EXTRA", "").split()
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"] + EXTRA
 PLAIN = ["capi.cu", "gram.cu", "reduce_kernels.cu", "solve.cu", "eigh.cu", "eigh_blocked.cu", "observables.cu", "particles.cu"]
 
 

@@ -396,8 +396,19 @@ __global__ void __launch_bounds__(kPT, 1) tridiag_panel_kernel(const __grid_cons
           double zsum = 0.0;
           const int r = sl < S ? row_of_slot(sl) : n;
           if (r > j && r < n) {
-#pragma unroll 4
-            for (int bb = kp; bb < G; bb += 8) zsum += __ldcg(a.Z + (size_t)bb * ld + r);
+            // up to 160 CTAs: 20 loads per lane, straight-line so that they are all in flight together
+            double z0 = 0.0, z1 = 0.0, z2 = 0.0, z3 = 0.0;
+            const double* zc = a.Z + r;
+#pragma unroll
+            for (int u = 0; u < 20; u += 4) {
+              const int b0 = kp + 8 * u;
+              if (b0 < G) z0 += __ldcg(zc + (size_t)b0 * ld);
+              if (b0 + 8 < G) z1 += __ldcg(zc + (size_t)(b0 + 8) * ld);
+              if (b0 + 16 < G) z2 += __ldcg(zc + (size_t)(b0 + 16) * ld);
+              if (b0 + 24 < G) z3 += __ldcg(zc + (size_t)(b0 + 24) * ld);
+            }
+            for (int bb = kp + 160; bb < G; bb += 8) z0 += __ldcg(zc + (size_t)bb * ld);
+            zsum = (z0 + z1) + (z2 + z3);
           }
 #pragma unroll
           for (int o = 4; o > 0; o >>= 1) zsum += __shfl_xor_sync(0xffffffffu, zsum, o);
