@@ -109,6 +109,7 @@ struct PanelArgs {
   double* Y;               // [2 nb][ld]: rows k: w_k, rows nb + k: v_k, zero for index < j1
   double* Z;               // [grid][ld] column-part partial products of the symmetric mat-vec (NULL: full rows only)
   int sym_min_m;           // columns with a trailing size >= this read only the lower triangle
+  int zs_global;           // the column-part accumulator of a CTA lives in its row of Z (large n: no room in shared memory)
   long long* prof;         // optional per-phase cycle counters of CTA 0 (VMCPDE_PANEL_PROFILE)
   unsigned* bar;           // barrier counters
   unsigned epoch0;         // barrier epochs completed before this launch
@@ -143,7 +144,9 @@ __global__ void __launch_bounds__(kPT, 1) tridiag_panel_kernel(const __grid_cons
   double* ypart = rowW + nb;        // [S / 4][16][4]
   double* anext = ypart + S * 16;   // [S]
   double* red = anext + S;          // [64]
-  double* zs = red + 64;            // [nv] (symmetric mode only)
+  // column-part accumulator of the symmetric mode: [nv] in shared memory, or this CTA's own row of Z when v already
+  // fills shared memory (n > ~12k); every 64-column segment is touched by one warp only, so plain loads/stores suffice
+  double* zs = a.zs_global ? a.Z + (size_t)b * ld : red + 64;
 
   auto row_of_slot = [&](int s) { return (b + (s >> 2) * G) * kRC + (s & 3); };
   const int nq = (n + kRC - 1) / kRC;                   // ownership chunks
@@ -203,7 +206,7 @@ __global__ void __launch_bounds__(kPT, 1) tridiag_panel_kernel(const __grid_cons
       __syncthreads();  // every thread has read alpha
       for (int c = j + 1 + tid; c < n; c += kPT) vs[c] = c == j + 1 ? 1.0 : vs[c] * scale;
       const bool sym = a.Z != nullptr && m >= a.sym_min_m;
-      if (sym) for (int c = (j & ~1) + tid; c < nv; c += kPT) zs[c] = 0.0;
+      if (sym) for (int c = (j & ~1) + tid; c < (a.zs_global ? ((n + 1) & ~1) : nv); c += kPT) zs[c] = 0.0;
       __syncthreads();
       for (int c = wlo + tid; c < whi; c += kPT) {
         const double val = vs[c];
@@ -367,7 +370,7 @@ __global__ void __launch_bounds__(kPT, 1) tridiag_panel_kernel(const __grid_cons
         double* zrow = a.Z + (size_t)b * ld;
         for (int c = j + 1 + tid; c < n; c += kPT) {
           const double z = zs[c];
-          zrow[c] = z;
+          if (!a.zs_global) zrow[c] = z;   // global accumulator: already in place
           yvp = fma(z, vs[c], yvp);
         }
       }
@@ -657,7 +660,8 @@ size_t al256(size_t x) { return (x + 255) / 256 * 256; }
 struct BlockedPlan {
   int nb = 0, S = 0, grid = 0;
   size_t smem = 0;
-  bool sym = false;   // room for the column-part accumulator of the symmetric mat-vec
+  bool sym = false;        // symmetric (lower-triangle) mat-vec available
+  bool zs_global = false;  // ... with its column-part accumulator in global memory
 };
 
 static bool plan_panel(int n, BlockedPlan* p) {
@@ -674,7 +678,11 @@ static bool plan_panel(int n, BlockedPlan* p) {
     const size_t doubles = (size_t)nv + 2 * (size_t)S * (nb + 1) + 3 * S + 4 * nb + (size_t)S * 16 + 64;
     if (doubles * 8 <= (size_t)max_smem) {
       p->nb = nb; p->S = S; p->grid = G; p->smem = doubles * 8;
-      if (nb == 64 && (doubles + nv) * 8 <= (size_t)max_smem && !getenv("VMCPDE_EIGH_NOSYM")) { p->sym = true; p->smem = (doubles + nv) * 8; }
+      if (!getenv("VMCPDE_EIGH_NOSYM")) {
+        p->sym = true;
+        if (nb == 64 && (doubles + nv) * 8 <= (size_t)max_smem && !getenv("VMCPDE_EIGH_ZS_GLOBAL")) p->smem = (doubles + nv) * 8;
+        else p->zs_global = true;
+      }
       return true;
     }
   }
@@ -736,6 +744,7 @@ int tridiag_blocked(double* A, int n, int ld, double* d, double* e, double* tau,
   a.prof = prof;
   VMC_CUDA_CHECK(cudaMemsetAsync(a.acol, 0, (size_t)(wp - (uint8_t*)a.acol), s));
   a.Z = p.sym ? (double*)take((size_t)G * ld * 8) : nullptr;
+  a.zs_global = p.zs_global ? 1 : 0;
   a.sym_min_m = 1536;
   if (const char* e_ = getenv("VMCPDE_EIGH_SYM_MIN_M")) a.sym_min_m = atoi(e_);
   VMC_CUDA_CHECK(cudaFuncSetAttribute(tridiag_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
