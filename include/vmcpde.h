@@ -155,6 +155,10 @@ int vmcpde_diag_shift(const double* S, double* S_shifted, int32_t Pp, int32_t P,
  * (ldx) and Y [K x N] (ldy) row-major.  M, N multiples of 128, K of 16 (pad with zeros). */
 int vmcpde_gemm_tn(const double* X, int64_t ldx, const double* Y, int64_t ldy, double* Out, int64_t ldo,
                    int32_t M, int32_t N, int64_t K, double alpha, double beta, vmcpde_stream stream);
+/* Split-K form for few output tiles and a long contraction: slice s of the K range -> Part + s * M * ldo (alpha 1, beta 0);
+ * the caller adds the `splits` (1..16) slices. */
+int vmcpde_gemm_tn_splitk(const double* X, int64_t ldx, const double* Y, int64_t ldy, double* Part, int64_t ldo,
+                          int32_t M, int32_t N, int64_t K, int32_t splits, vmcpde_stream stream);
 /* Upper-triangular 128x128 tiles of Out = alpha * X^T X + beta * Out on the same pipeline (X [K x M] row-major, M multiple
  * of 128, K of 16); the lower tiles of Out are not touched. */
 int vmcpde_syrk_tn(const double* X, int64_t ldx, double* Out, int64_t ldo, int32_t M, int64_t K, double alpha,

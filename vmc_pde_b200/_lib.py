@@ -38,6 +38,7 @@ SIGNATURES = {
     "vmcpde_sym_finalize": (C.c_int, [_vp, _i32, _dbl, _vp]),
     "vmcpde_diag_shift": (C.c_int, [_vp, _vp, _i32, _i32, _dbl, _vp]),
     "vmcpde_dmma_peak": (C.c_int, [C.POINTER(_dbl)]),
+    "vmcpde_gemm_tn_splitk": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i64, _i32, _vp]),
     "vmcpde_syrk_tn": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i64, _dbl, _dbl, _vp]),
     "vmcpde_gemm_tn": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i64, _dbl, _dbl, _vp]),
     "vmcpde_eigh_workspace_bytes": (C.c_int, [_i32, _i32, C.POINTER(C.c_size_t)]),

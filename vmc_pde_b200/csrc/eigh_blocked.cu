@@ -19,6 +19,8 @@
 
 extern "C" int vmcpde_gemm_tn(const double* X, int64_t ldx, const double* Y, int64_t ldy, double* Out, int64_t ldo,
                               int32_t M, int32_t N, int64_t K, double alpha, double beta, vmcpde_stream stream);
+extern "C" int vmcpde_gemm_tn_splitk(const double* X, int64_t ldx, const double* Y, int64_t ldy, double* Part, int64_t ldo,
+                                     int32_t M, int32_t N, int64_t K, int32_t splits, vmcpde_stream stream);
 
 namespace vmc {
 
@@ -562,6 +564,17 @@ __global__ void __launch_bounds__(256) transpose_cols_kernel(const double* __res
   for (int r = ty; r < 32; r += 8) B[(size_t)(cc + r) * ld + r0 + tx] = tile[tx][r];
 }
 
+// G[r][c] = sum_s Part[s][r][c] for the 128 x ncols split-K slices of Y^T V (fixed order)
+__global__ void __launch_bounds__(256) sum_slices_kernel(const double* __restrict__ part, int splits, int ld, int ncols,
+                                                         double* __restrict__ G) {
+  const int r = blockIdx.y;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncols; c += gridDim.x * blockDim.x) {
+    double sacc = 0.0;
+    for (int q = 0; q < splits; ++q) sacc += part[((size_t)q * 128 + r) * ld + c];
+    G[(size_t)r * ld + c] = sacc;
+  }
+}
+
 // Partial Gram of one 128-reflector block over a slice of 1024 coordinates:
 // part[blk][slice][k][k'] = sum_{c in slice} AT[c][128 blk + k] AT[c][128 blk + k']   (DMMA, 8 warps x 64x32)
 constexpr int kBK = 128;       // reflectors per back-transform block
@@ -713,7 +726,7 @@ int blocked_tridiag_launches(int n) {
   const int panels = (n + p.nb - 1) / p.nb;
   return 2 * panels - 1;
 }
-int blocked_backtransform_launches(int n) { return 5 + 3 * ((n + kBK - 1) / kBK); }
+int blocked_backtransform_launches(int n) { return 5 + 4 * ((n + kBK - 1) / kBK); }   // upper bound (split-K adds one per block)
 
 // A: np x ld work matrix (np = n rounded up to 128 rows must be allocated), destroyed: on exit row j holds v_j.
 int tridiag_blocked(double* A, int n, int ld, double* d, double* e, double* tau, void* scratch, size_t scratch_bytes,
@@ -789,7 +802,8 @@ int tridiag_blocked(double* A, int n, int ld, double* d, double* e, double* tau,
 size_t blocked_backtransform_scratch_bytes(int n, int ld) {
   const int np = (n + 127) / 128 * 128, nblk = np / kBK;
   const int max_slices = (np + kSlice - 1) / kSlice;
-  return al256((size_t)nblk * max_slices * kBK * kBK * 8) + al256((size_t)nblk * kBK * kBK * 8) + 2 * al256((size_t)kBK * ld * 8);
+  return al256((size_t)nblk * max_slices * kBK * kBK * 8) + al256((size_t)nblk * kBK * kBK * 8) + 2 * al256((size_t)kBK * ld * 8) +
+         al256((size_t)16 * kBK * ld * 8);   // split-K slices of Y^T V
 }
 
 // V = H_0 ... H_{n-3} Z.  ZT (np x ld, rows = eigenvectors of the tridiagonal, zero padded) is consumed;
@@ -812,6 +826,11 @@ int backtransform_blocked(double* A, const double* tau, int n, int ld, const dou
   double* Tt = (double*)take((size_t)nblk * kBK * kBK * 8);
   double* G1 = (double*)take((size_t)kBK * ld * 8);
   double* G2 = (double*)take((size_t)kBK * ld * 8);
+  double* Gs = (double*)take((size_t)16 * kBK * ld * 8);
+  // Y^T V has only ncols / 128 output tiles: split its contraction so that tiles x splits fills the SMs
+  const int g1_tiles = ncols / 128;
+  int splits = g1_tiles >= num_sms() / 2 ? 1 : min(16, num_sms() / g1_tiles);
+  if (getenv("VMCPDE_BT_NOSPLIT")) splits = 1;
   block_gram_kernel<<<dim3(max_slices, nblk), 256, 0, s>>>(AT, ld, np, part, max_slices);
   const size_t lsm = (size_t)kBK * (kBK + 1) * 8;
   VMC_CUDA_CHECK(cudaFuncSetAttribute(larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
@@ -821,7 +840,11 @@ int backtransform_blocked(double* A, const double* tau, int n, int ld, const dou
   for (int blk = nblk - 1; blk >= 0; --blk) {
     const int c0 = blk * kBK, K = np - c0;
     // G1 = Y^T Zn  (128 x ncols), contraction over the coordinates c >= c0
-    if (int rc = vmcpde_gemm_tn(AT + (size_t)c0 * ld + c0, ld, Zc + (size_t)c0 * ld, ld, G1, ld, kBK, ncols, K, 1.0, 0.0, (vmcpde_stream)s)) return rc;
+    const int sp = min(splits, max(1, K / 256));   // at least 16 pipeline steps per slice
+    if (sp > 1) {
+      if (int rc = vmcpde_gemm_tn_splitk(AT + (size_t)c0 * ld + c0, ld, Zc + (size_t)c0 * ld, ld, Gs, ld, kBK, ncols, K, sp, (vmcpde_stream)s)) return rc;
+      sum_slices_kernel<<<dim3(max(1, min(8, ncols / 256)), kBK), 256, 0, s>>>(Gs, sp, ld, ncols, G1);
+    } else if (int rc = vmcpde_gemm_tn(AT + (size_t)c0 * ld + c0, ld, Zc + (size_t)c0 * ld, ld, G1, ld, kBK, ncols, K, 1.0, 0.0, (vmcpde_stream)s)) return rc;
     // G2 = T G1
     if (int rc = vmcpde_gemm_tn(Tt + (size_t)blk * kBK * kBK, kBK, G1, ld, G2, ld, kBK, ncols, kBK, 1.0, 0.0, (vmcpde_stream)s)) return rc;
     // Zn[c0:, range] -= Y G2

@@ -35,7 +35,7 @@ constexpr int kGramThreads = (kConsumerWarps + 4) * 32;  // 2 consumer warpgroup
 constexpr int kPanelBytes = kBM * kKC * 8;  // 16 KB
 constexpr int kWBytes = kKC * 8;            // 128 B of row weights
 constexpr int kStageBytes = 2 * kPanelBytes + 1024;  // A, B, weights (padded to keep 1 KB alignment)
-constexpr int kMaxMats = 4;
+constexpr int kMaxMats = 16;   // weighted matrices of one SYRK launch (<= 4 are used) or K-slices of a split-K product
 
 struct GramArgs {
   double* S[kMaxMats];
@@ -46,6 +46,7 @@ struct GramArgs {
   int Pp;         // leading dimension of the outputs
   int full;       // 0: upper-triangular tile pairs of X^T X ; 1: all tiles of X^T Y (second tensor map)
   int super;      // supertile edge of the SYRK enumeration (tiles)
+  int ksplit;     // full mode only: the n_mats "matrices" are K-slices of one product, slice m -> its own output S[m]
   int wave_sync;  // 1: producers rendezvous at every work item (keeps the CTAs of a wave inside one L2 window)
   double alpha, beta;  // out = alpha * acc + beta * out
   long long n;    // contraction length (samples)
@@ -177,7 +178,12 @@ gram_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
         const bool diag = !args.full && (ti == tj);
         const double* w = args.w[mat];
         const uint32_t bytes = kPanelBytes + (diag ? 0 : kPanelBytes) + (w ? kWBytes : 0);
-        for (int k = 0; k < k_iters; ++k) {
+        int k_begin = 0, k_end = k_iters;
+        if (args.ksplit) {
+          const int kper = (k_iters + args.n_mats - 1) / args.n_mats;
+          k_begin = mat * kper; k_end = min(k_iters, k_begin + kper);
+        }
+        for (int k = k_begin; k < k_end; ++k) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* st = smem + stage * kStageBytes;
           mbar_expect_tx(&full[stage], bytes);
@@ -221,7 +227,12 @@ gram_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
 #pragma unroll
       for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
-    for (int k = 0; k < k_iters; ++k) {
+    int k_begin = 0, k_end = k_iters;
+    if (args.ksplit) {
+      const int kper = (k_iters + args.n_mats - 1) / args.n_mats;
+      k_begin = mat * kper; k_end = min(k_iters, k_begin + kper);
+    }
+    for (int k = k_begin; k < k_end; ++k) {
       mbar_wait(&full[stage], phase);
       const uint8_t* st = smem + stage * kStageBytes;
       const uint8_t* pa = st + a_cg0;
@@ -330,7 +341,7 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_gram(const double* 
   VMC_REQUIRE(Pp > 0 && Pp % 128 == 0, "vmcpde_gram: Pp must be a positive multiple of 128");
   VMC_REQUIRE(ldo >= Pp && ldo % 2 == 0, "vmcpde_gram: ldo must be even and >= Pp");
   VMC_REQUIRE(n >= 0 && n % kKC == 0, "vmcpde_gram: n must be a multiple of 16");
-  VMC_REQUIRE(n_mats >= 1 && n_mats <= kMaxMats, "vmcpde_gram: n_mats must be in [1,4]");
+  VMC_REQUIRE(n_mats >= 1 && n_mats <= 4, "vmcpde_gram: n_mats must be in [1,4]");
   VMC_REQUIRE(((uintptr_t)O & 15) == 0, "vmcpde_gram: O must be 16-byte aligned");
   if (n == 0) return 0;
   GramArgs a{};
@@ -421,6 +432,34 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_gemm_tn(const doubl
   if (n_items < grid) grid = (int)n_items;
   gram_kernel<<<grid, kGramThreads, smem, (cudaStream_t)stream>>>(mx, my, a);
   VMC_LAUNCH_CHECK("gram_kernel(gemm_tn)");
+  return 0;
+}
+
+// Split-K form of vmcpde_gemm_tn for products with few output tiles and a long contraction (the Y^T V products of the
+// back-transformation): slice s of the K range goes to its own output Part + s * M * ldo (alpha = 1, beta = 0), so
+// tiles x splits work items fill the GPU; the caller adds the slices (fixed order).  splits in [1, 16].
+extern "C" __attribute__((visibility("default"))) int vmcpde_gemm_tn_splitk(const double* X, int64_t ldx, const double* Y, int64_t ldy, double* Part,
+                                                                             int64_t ldo, int32_t M, int32_t N, int64_t K, int32_t splits,
+                                                                             vmcpde_stream stream) {
+  using namespace vmc;
+  VMC_REQUIRE(X && Y && Part, "vmcpde_gemm_tn_splitk: null pointer");
+  VMC_REQUIRE(M > 0 && N > 0 && M % 128 == 0 && N % 128 == 0 && K > 0 && K % kKC == 0, "vmcpde_gemm_tn_splitk: M, N multiples of 128 and K of 16 required");
+  VMC_REQUIRE(ldx >= M && ldy >= N && ldo >= N && ldx % 2 == 0 && ldy % 2 == 0 && ldo % 2 == 0 && ldo <= 0x7fffffff, "vmcpde_gemm_tn_splitk: bad leading dimensions");
+  VMC_REQUIRE(splits >= 1 && splits <= kMaxMats, "vmcpde_gemm_tn_splitk: splits must be in [1, 16]");
+  GramArgs a{};
+  for (int sidx = 0; sidx < splits; ++sidx) { a.S[sidx] = Part + (size_t)sidx * M * ldo; a.w[sidx] = nullptr; }
+  a.n_mats = splits; a.tiles = M / 128; a.tiles_n = N / 128; a.Pp = (int)ldo; a.n = K; a.full = 1; a.ksplit = 1; a.super = 1;
+  a.alpha = 1.0; a.beta = 0.0;
+  CUtensorMap mx, my;
+  if (int rc = make_panel_tensor_map(&mx, X, K, ldx, M)) return rc;
+  if (int rc = make_panel_tensor_map(&my, Y, K, ldy, N)) return rc;
+  const size_t smem = gram_smem_bytes();
+  VMC_CUDA_CHECK(cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long n_items = (long long)splits * a.tiles * a.tiles_n;
+  int grid = num_sms();
+  if (n_items < grid) grid = (int)n_items;
+  gram_kernel<<<grid, kGramThreads, smem, (cudaStream_t)stream>>>(mx, my, a);
+  VMC_LAUNCH_CHECK("gram_kernel(gemm_tn_splitk)");
   return 0;
 }
 
