@@ -174,6 +174,44 @@ def test_gram_properties_large(L):
     assert torch.equal(S[0], S[0].T)
 
 
+def test_gram_tail_split_syrk_and_splitk_products(L):
+    """The partly filled last round of work items is split along the samples (513 items on 148 CTAs: 69 tail items, 2
+    slices each, added in slice order): every tile against an independent FP64 product, bit-for-bit repeatable.  Plus the
+    two other forms of the pipeline: vmcpde_syrk_tn (scaled, upper tiles only) and vmcpde_gemm_tn_splitk."""
+    from vmc_pde_b200 import _lib
+    f64 = torch.float64
+    n, Pp = 8192, 2304
+    O = torch.randn(n, Pp, device=dev(), dtype=f64)
+    w1, w2 = torch.rand(n, device=dev(), dtype=f64), torch.rand(n, device=dev(), dtype=f64)
+    runs = []
+    for _ in range(2):
+        S = [torch.zeros(Pp, Pp, device=dev(), dtype=f64) for _ in range(3)]
+        _lib.check(L.vmcpde_gram(_lib.ptr(O), n, Pp, Pp, 3, _lib.ptr_array([None, w1, w2]), _lib.ptr_array(S), _lib.stream()))
+        runs.append(S)
+    up = torch.triu(torch.ones(Pp, Pp, device=dev(), dtype=torch.bool))
+    blockup = up.view(Pp // 128, 128, Pp // 128, 128).any(dim=3).any(dim=1)                      # computed tiles
+    tilemask = blockup.repeat_interleave(128, 0).repeat_interleave(128, 1)
+    for S, w in zip(runs[0], (None, w1, w2)):
+        ref = (O if w is None else O * w[:, None]).T @ O
+        assert float(((S - ref) * tilemask).abs().max()) < 1e-11 * float(ref.abs().max())
+    assert all(torch.equal(a, b) for a, b in zip(runs[0], runs[1]))
+    # SYRK form with a scale: Out(upper tiles) = alpha X^T X + beta Out
+    K, M = 256, 640
+    X = torch.randn(K, M, device=dev(), dtype=f64); Out = torch.randn(M, M, device=dev(), dtype=f64); Out0 = Out.clone()
+    _lib.check(L.vmcpde_syrk_tn(_lib.ptr(X), M, _lib.ptr(Out), M, M, K, -0.5, 2.0, _lib.stream()))
+    ref = -0.5 * X.T @ X + 2.0 * Out0
+    tm = torch.triu(torch.ones(M // 128, M // 128, device=dev(), dtype=torch.bool)).repeat_interleave(128, 0).repeat_interleave(128, 1)
+    assert float(((Out - ref) * tm).abs().max()) < 1e-12 * float(ref.abs().max()) and torch.equal(Out[~tm], Out0[~tm])
+    # split-K: slices of the contraction in separate outputs
+    K, M, N, sp = 1040, 128, 256, 5
+    X = torch.randn(K, M, device=dev(), dtype=f64); Y = torch.randn(K, N, device=dev(), dtype=f64)
+    Part = torch.full((sp, M, N), float("nan"), device=dev(), dtype=f64)
+    _lib.check(L.vmcpde_gemm_tn_splitk(_lib.ptr(X), M, _lib.ptr(Y), N, _lib.ptr(Part), N, M, N, K, sp, _lib.stream()))
+    assert relerr(Part.sum(0), X.T @ Y) < 1e-13
+    kper = -(-(K // 16) // sp) * 16
+    assert relerr(Part[1], X[kper:2 * kper].T @ Y[kper:2 * kper]) < 1e-13
+
+
 def test_gemm_tn(L):
     from vmc_pde_b200 import _lib
     K, M, N = 528, 256, 384

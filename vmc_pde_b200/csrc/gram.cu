@@ -47,6 +47,8 @@ struct GramArgs {
   int full;       // 0: upper-triangular tile pairs of X^T X ; 1: all tiles of X^T Y (second tensor map)
   int super;      // supertile edge of the SYRK enumeration (tiles)
   int ksplit;     // full mode only: the n_mats "matrices" are K-slices of one product, slice m -> its own output S[m]
+  int tail_ks;    // SYRK mode: the n_items % grid items of the last, partly filled round are each split into tail_ks K-slices
+                  // (0: off) so that the round costs 1 / tail_ks of an item; slices add their result in slice order
   int wave_sync;  // 1: producers rendezvous at every work item (keeps the CTAs of a wave inside one L2 window)
   double alpha, beta;  // out = alpha * acc + beta * out
   long long n;    // contraction length (samples)
@@ -55,6 +57,8 @@ struct GramArgs {
 // Arrival counter of the per-wave rendezvous of the SYRK producers (performance only, see gram_kernel); zeroed before
 // every launch that uses it.  One per device; launches that use it must not overlap on one device.
 __device__ unsigned g_wave_counter;
+// Turn counters of the split tail items (see gram_kernel): g_tail_turn[t] = number of K-slices of tail item t already added.
+__device__ unsigned g_tail_turn[256];
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -150,6 +154,23 @@ gram_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
   const long long n_items = args.full ? (long long)args.n_mats * args.tiles * args.tiles_n
                                       : (long long)args.n_mats * args.tiles * (args.tiles + 1) / 2;
   const int k_iters = (int)(args.n / kKC);
+  // Work units of this CTA: its items of the full rounds, then (tail_ks > 0) one K-slice of an item of the last round.
+  const long long main_items = args.tail_ks ? n_items - n_items % gridDim.x : n_items;
+  const int tail_items = (int)(n_items - main_items);
+  auto get_unit = [&](long long u, long long& item, int& kb, int& ke) -> bool {   // tail unit <=> item >= main_items
+    item = (long long)blockIdx.x + u * gridDim.x;
+    kb = 0; ke = k_iters;
+    if (item < main_items) return true;
+    const long long u_main = main_items > (long long)blockIdx.x ? (main_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    if (args.tail_ks && u == u_main && (int)blockIdx.x < tail_items * args.tail_ks) {
+      const int tidx = (int)blockIdx.x / args.tail_ks, tslice = (int)blockIdx.x % args.tail_ks;
+      item = main_items + tidx;
+      const int kper = (k_iters + args.tail_ks - 1) / args.tail_ks;
+      kb = tslice * kper; ke = min(k_iters, kb + kper);
+      return true;
+    }
+    return false;
+  };
 
   if (warp >= kConsumerWarps) {
     // ===== producer warpgroup: hands its registers to the consumers; one elected lane drives TMA =====
@@ -158,8 +179,10 @@ gram_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
       int stage = 0;
       uint32_t phase = 0;
       unsigned wave_target = 0;
-      for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
-        if (args.wave_sync) {
+      for (long long u = 0;; ++u) {
+        long long item; int k_begin, k_end;
+        if (!get_unit(u, item, k_begin, k_end)) break;
+        if (args.wave_sync && item < main_items) {
           // All CTAs take items of equal length, but they drift apart over a 1.5 s launch and then miss each other's panels
           // in L2.  The producers therefore meet before every item.  This is an optimisation only: the wait is bounded,
           // so nothing depends on the CTAs being co-resident.
@@ -178,7 +201,6 @@ gram_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
         const bool diag = !args.full && (ti == tj);
         const double* w = args.w[mat];
         const uint32_t bytes = kPanelBytes + (diag ? 0 : kPanelBytes) + (w ? kWBytes : 0);
-        int k_begin = 0, k_end = k_iters;
         if (args.ksplit) {
           const int kper = (k_iters + args.n_mats - 1) / args.n_mats;
           k_begin = mat * kper; k_end = min(k_iters, k_begin + kper);
@@ -216,7 +238,9 @@ gram_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
 
   int stage = 0;
   uint32_t phase = 0;
-  for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+  for (long long u = 0;; ++u) {
+    long long item; int k_begin, k_end;
+    if (!get_unit(u, item, k_begin, k_end)) break;
     int mat, ti, tj;
     decode_item(item, args, mat, ti, tj);
     const bool diag = !args.full && (ti == tj);
@@ -227,7 +251,6 @@ gram_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
 #pragma unroll
       for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
-    int k_begin = 0, k_end = k_iters;
     if (args.ksplit) {
       const int kper = (k_iters + args.n_mats - 1) / args.n_mats;
       k_begin = mat * kper; k_end = min(k_iters, k_begin + kper);
@@ -264,21 +287,56 @@ gram_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
       if (++stage == kStages) { stage = 0; phase ^= 1; }
     }
 
-    // epilogue: S[ti*128 + m][tj*128 + n] += acc   (single writer per tile and launch)
+    // epilogue: S[ti*128 + m][tj*128 + n] += acc   (single writer per tile and launch; the K-slices of a tail item
+    // take turns in slice order, so the sum is still formed in a fixed order)
     double* S = args.S[mat];
     const long long row0 = (long long)ti * kBM + wm * 64 + g;
     const long long col0 = (long long)tj * kBN + wn * 32 + 2 * t;
+    bool atomic_fallback = false;
+    const int tslice = (args.tail_ks && item >= main_items) ? (int)blockIdx.x % args.tail_ks : -1;
+    const int tidx = tslice >= 0 ? (int)blockIdx.x / args.tail_ks : 0;
+    if (tslice >= 0) {
+      volatile int& s_fallback = *(volatile int*)(empty + kStages);   // 8 spare bytes behind the mbarriers
+      if (threadIdx.x == 0) {
+        int fb = 0;
+        if (tslice > 0) {
+          const long long t0 = clock64();
+          unsigned turn;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(turn) : "l"(&g_tail_turn[tidx]) : "memory");
+          } while (turn < (unsigned)tslice && clock64() - t0 < 200000000ll);   // ~0.1 s: never reached when the CTAs are co-resident
+          fb = turn < (unsigned)tslice;
+        }
+        s_fallback = fb;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 consumer warps
+      atomic_fallback = s_fallback != 0;
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         double2* p = (double2*)(S + (row0 + i * 8) * args.Pp + col0 + j * 8);
+        if (atomic_fallback) {   // a predecessor slice has not shown up: stay correct, give up the fixed order
+          atomicAdd(&p->x, args.alpha * acc[i][j][0]);
+          atomicAdd(&p->y, args.alpha * acc[i][j][1]);
+          continue;
+        }
         double2 v = make_double2(0.0, 0.0);
-        if (args.beta != 0.0) { v = *p; v.x *= args.beta; v.y *= args.beta; }
+        const double beta = tslice > 0 ? 1.0 : args.beta;   // later slices add onto what the earlier ones wrote
+        if (beta != 0.0) { v = *p; v.x *= beta; v.y *= beta; }
         v.x = fma(args.alpha, acc[i][j][0], v.x);
         v.y = fma(args.alpha, acc[i][j][1], v.y);
         *p = v;
       }
+    if (tslice >= 0) {
+      __threadfence();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (threadIdx.x == 0) {
+        if (atomic_fallback) atomicAdd(&g_tail_turn[tidx], 1u);
+        else asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&g_tail_turn[tidx]), "r"((unsigned)(tslice + 1)) : "memory");
+      }
+    }
   }
 }
 
@@ -314,7 +372,7 @@ int make_panel_tensor_map(CUtensorMap* map, const double* X, long long n, long l
   return 0;
 }
 
-static size_t gram_smem_bytes() { return (size_t)kStages * kStageBytes + 2 * kStages * sizeof(uint64_t); }
+static size_t gram_smem_bytes() { return (size_t)kStages * kStageBytes + 2 * kStages * sizeof(uint64_t) + 16; }
 
 // DMMA issue-rate microbenchmark: register-resident chains, no memory traffic.
 __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) {
@@ -370,6 +428,22 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_gram(const double* 
   // 0.41 TB (L2 hit rate 52 % -> 80 %) but costs 1.2 % of time -- the kernel is DMMA bound and the slack that lets fast CTAs
   // run ahead is exactly what a rendezvous removes -- so it is opt-in (VMCPDE_GRAM_WAVE_SYNC=1).
   a.wave_sync = (n_items > grid && n >= 4096 && getenv("VMCPDE_GRAM_WAVE_SYNC")) ? 1 : 0;
+  // The last round is usually partly filled (C3: 6240 items on 148 CTAs = 42 rounds + 24 items): split its items along K so
+  // that all CTAs share it.  Needs rounds of equal cost (beta = 1 accumulation, long items) to be worth it.
+  a.tail_ks = 0;
+  {
+    const long long rem = n_items % grid;
+    if (n_items > grid && rem > 0 && rem * 2 <= grid && n / kKC >= 256 && !getenv("VMCPDE_GRAM_NOTAIL")) {
+      int ks = (int)(grid / rem);
+      if (ks > 8) ks = 8;
+      if (rem <= 256) a.tail_ks = ks;
+    }
+  }
+  if (a.tail_ks) {
+    void* tt = nullptr;
+    VMC_CUDA_CHECK(cudaGetSymbolAddress(&tt, g_tail_turn));
+    VMC_CUDA_CHECK(cudaMemsetAsync(tt, 0, 256 * sizeof(unsigned), (cudaStream_t)stream));
+  }
   if (a.wave_sync) {
     void* ctr = nullptr;
     VMC_CUDA_CHECK(cudaGetSymbolAddress(&ctr, g_wave_counter));
