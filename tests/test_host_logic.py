@@ -153,3 +153,16 @@ def test_two_rank_reductions_over_gloo():
         assert np.allclose(r["packed"], np.concatenate([full.sum(0), (full ** 2).sum(0)]))
         assert np.array_equal(r["bcast"], np.arange(4.0))
     assert [r["spp"] for r in res] == [6, 5] and [r["fsid"] for r in res] == [0, 6]
+
+
+def test_bench_reference_arm_runs_on_the_cpu():
+    """bench.py --impl reference (the oracle port timed on the host cores): a reduced sample goes through every section
+    (sampling, local terms, Grams, eigh block, EO@V) and extrapolates to a positive step time."""
+    import importlib.util, pathlib
+    spec = importlib.util.spec_from_file_location("bench", pathlib.Path(__file__).resolve().parents[1] / "bench.py")
+    bench = importlib.util.module_from_spec(spec); spec.loader.exec_module(bench)
+    sec, parts = bench.cpu_step_estimate(n_s=64, p_s=256)
+    assert sec > 0 and set(parts) == {"sampling_s", "local_terms_s", "two_grams_and_F_s", "eigh_s", "EO_at_V_s"}
+    assert all(v >= 0 for v in parts.values())
+    cfg = bench.workload_config(4)
+    assert cfg["num_params"] == 8187 and cfg["n_samples"] == 2 ** 18 and "workload" in cfg
