@@ -105,6 +105,31 @@ def init_params(spec, seed=1):
     return theta
 
 
+def init_params_flax(spec, key):
+    """`mynet.init(key, zeros(d))` of var_state.py:123 in flax 0.3.6 / jax 0.2.18 (both unvendored; restated from the
+    published sources): module key = parent key folded with sha1(module name) (Scope.push), parameter key = module key
+    folded with the creation counter (Scope.make_rng; Dense creates 'kernel' first -> 1), kernel_init = net.py:39-41 on
+    jax.nn.initializers.uniform() = 0.01 * random.uniform(key, shape, float32).  `key` is the key left after the
+    index-split loop (make_index_splits(...)[2]).
+    PINNED: with this stream the 50 largest eigenvalues of S of the reference's stored d=6, P=411 run agree to 4e-3
+    (a fresh Monte-Carlo draw moves them by 3-7 %, a different init stream by 26 %); tests/test_reference_pins.py."""
+    sl, P = spec.slices()
+    theta = np.zeros(P)
+    nl = len(spec.hidden)
+    for name, (a, b, shape) in sl.items():
+        if not name.endswith("kernel"):
+            continue
+        parts = name.split("/")
+        k = threefry.fold_in_str(key, "myINN")
+        for part in parts[:-1]:
+            k = threefry.fold_in_str(k, part)
+        k = threefry.fold_in(k, 1)
+        scale = 1e-5 if parts[-2] == f"Dense_{nl}" else 1.0
+        u = threefry.uniform01(k, b - a, np.float32) * np.float32(0.01)
+        theta[a:b] = (np.float32(2 * scale) * (u / np.float32(0.01) - np.float32(0.5))).astype(np.float64)
+    return theta
+
+
 # ---------------------------------------------------------------------------- model (torch)
 def build_L(theta, spec, sl):
     """util.py:21-26 without the final L@L.T: strict upper from triu_indices(d,1) row-major + diag(exp)."""

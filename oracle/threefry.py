@@ -8,8 +8,11 @@ published algorithm (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3
 Threefry-2x32 with 20 rounds) and JAX's counter layout (jax/_src/random.py of that release:
 PRNGKey, _threefry_split, threefry_2x32, _random_bits, _uniform, _normal_real, _shuffle).
 
-Pins: Random123 known-answer vectors and jax.random.split(PRNGKey(0)),
-jax.random.uniform(PRNGKey(0)) == 0.41845703 (tests/test_oracle_rng.py).
+Pins: Random123 known-answer vectors, jax.random.split(PRNGKey(0)), jax.random.uniform(PRNGKey(0)) == 0.41845703
+(tests/test_oracle.py), and -- reference-held -- the stored outputs of the reference's own JAX runs
+(tests/golden/ref_*.npz, tests/test_reference_pins.py): `normal(PRNGKey(0), (10^4, 6))` reproduces the t=0 record of
+paper_plot/data_phaseSpace/Wiener/*/infos.hdf5 (mean, covariance, ball counts) to 1e-14, and split / per-particle
+split / normal reproduce all 1201 records of the stored Wiener trajectory to round-off.
 """
 import numpy as np
 
@@ -100,6 +103,42 @@ def normal(key, size, dtype=np.float64):
     lo = np.nextafter(dtype(-1.0), dtype(0.0))
     u = uniform(key, size, lo, 1.0, dtype)
     return (dtype(np.sqrt(2)) * erfinv(u)).astype(dtype)
+
+
+def fold_in(key, data):
+    """jax.random.fold_in(key, data) = threefry_2x32(key, PRNGKey(data)), data a 32-bit integer."""
+    o0, o1 = threefry2x32(key[0], key[1], np.zeros(1, np.uint32), np.array([int(data) & 0xFFFFFFFF], np.uint32))
+    return np.array([o0[0], o1[0]], dtype=np.uint32)
+
+
+def fold_in_str(key, name):
+    """flax 0.3.6 flax/core/scope.py `_fold_in_str` (the unvendored dependency that seeds net.init, var_state.py:123):
+    fold in int.from_bytes(sha1(name)[:4], 'big')."""
+    import hashlib
+    return fold_in(key, int.from_bytes(hashlib.sha1(name.encode("utf-8")).digest()[:4], byteorder="big"))
+
+
+def split_each(keys, num):
+    """jax.vmap(lambda k: jax.random.split(k, num)) over an (N, 2) array of keys -> (N, num, 2)
+    (exact_dyn.py:71 under the vmap of :82)."""
+    keys = np.asarray(keys, dtype=np.uint32)
+    cnt = np.arange(2 * num, dtype=np.uint32)
+    o0, o1 = threefry2x32(keys[:, 0:1], keys[:, 1:2], cnt[None, :num], cnt[None, num:])
+    return np.concatenate([o0, o1], axis=1).reshape(-1, num, 2)
+
+
+def normal_each(keys, size):
+    """jax.vmap(lambda k: jax.random.normal(k, (size,))) in float64 over an (N, 2) array of keys -> (N, size)
+    (exact_dyn.py:59,66 under the vmap of :82)."""
+    from scipy.special import erfinv
+    keys = np.asarray(keys, dtype=np.uint32)
+    cnt = np.arange(2 * size, dtype=np.uint32)
+    o0, o1 = threefry2x32(keys[:, 0:1], keys[:, 1:2], cnt[None, :size], cnt[None, size:])
+    bits = (o0.astype(np.uint64) << np.uint64(32)) | o1.astype(np.uint64)
+    f = ((bits >> np.uint64(12)) | np.float64(1.0).view(np.uint64)).view(np.float64) - 1.0
+    lo = np.nextafter(np.float64(-1.0), np.float64(0.0))
+    u = np.maximum(lo, f * (np.float64(1.0) - lo) + lo)
+    return np.sqrt(2.0) * erfinv(u)
 
 
 def shuffle(key, n):

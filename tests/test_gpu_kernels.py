@@ -280,6 +280,41 @@ def test_eigh_blocked_path_edge_cases(L):
     check(S * 1e-150); check(S * 1e150)
 
 
+@pytest.mark.parametrize("n", [8187, 16385])
+def test_eigh_at_benchmark_sizes_against_the_library_solver(L, n):
+    """The sizes the benchmarks run (C3: P = 8187, C4: P = 16385) on a graded, numerically rank-deficient Gram matrix like
+    the S of a real run: every eigenvalue against cuSOLVER's syevd (torch.linalg.eigvalsh -- yardstick only, never on the
+    product path) to 1e-13 ||S||, the full orthogonality defect ||V^T V - I||_max and the full residual ||S V - V diag(ev)||_max."""
+    from vmc_pde_b200 import _lib
+    g = torch.Generator(device="cuda"); g.manual_seed(n)
+    rows = n // 2                                              # rank <= n/2: half of the spectrum is round-off, as in real runs
+    A = torch.randn(rows, n, device=dev(), dtype=torch.float64, generator=g)
+    A *= 10.0 ** (-6.0 * torch.arange(n, device=dev(), dtype=torch.float64) / n)
+    ld = L.vmcpde_padded_params(n)
+    S = torch.zeros(ld, ld, device=dev(), dtype=torch.float64)
+    S[:n, :n] = A.T @ A / rows
+    del A
+    S[:n, :n] = (S[:n, :n] + S[:n, :n].T) / 2
+    ref = torch.linalg.eigvalsh(S[:n, :n])
+    work = S.clone()
+    ev = torch.zeros(ld, device=dev(), dtype=torch.float64); VT = torch.zeros(ld, ld, device=dev(), dtype=torch.float64)
+    nb = C.c_size_t(0); _lib.check(L.vmcpde_eigh_workspace_bytes(n, ld, C.byref(nb)))
+    ws = torch.empty(nb.value, device=dev(), dtype=torch.uint8)
+    _lib.check(L.vmcpde_eigh(_lib.ptr(work), n, ld, _lib.ptr(ev), _lib.ptr(VT), _lib.ptr(ws), nb.value, _lib.stream()))
+    del work, ws
+    nrm = float(ref.abs().max())
+    assert bool((ev[1:n] >= ev[:n - 1]).all())
+    assert float((ev[:n] - ref).abs().max()) <= 1e-13 * nrm
+    V = VT[:n, :n].T
+    G = VT[:n, :n] @ V
+    G.diagonal().sub_(1.0)
+    assert float(G.abs().max()) < 5e-12
+    del G
+    R = S[:n, :n] @ V - V * ev[:n]
+    assert float(R.abs().max()) <= 5e-13 * nrm
+    assert int((ev[:n].abs() < 1e-11 * nrm).sum()) >= n // 2 - 8   # the null space is resolved as such
+
+
 def test_eigh_is_run_to_run_deterministic(L):
     """Fixed-order reductions and tagged messages: two runs on the same matrix agree bit for bit (blocked path, both
     mat-vec modes), and so do the replicated solves of a multi-GPU run."""

@@ -236,6 +236,12 @@ def test_driver_loop_like_main_py():
         infos["times"].append(t); infos["ev"].append(tdvpEq.ev); infos["snr"].append(tdvpEq.snr)
         infos["solver_res"].append(tdvpEq.solverResidual); infos["tdvp_error"].append(tdvpEq.tdvp_error)
         t += dt
+    # main.py:187-190 keeps the per-step objects: they must be snapshots, not views of a work buffer (JAX arrays are immutable)
+    assert not torch.equal(infos["ev"][0], infos["ev"][-1]) and not torch.equal(infos["snr"][0], infos["snr"][-1])
+    assert float(infos["solver_res"][0]) != float(infos["solver_res"][-1])
+    ev_last = infos["ev"][-1].clone()
+    tdvpEq(vs.get_parameters(), 0.0, psi=vs, evolutionEq=eq, nSamplesTDVP=2000, nSamplesObs=2000, timings=None)
+    assert torch.equal(infos["ev"][-1], ev_last)
     exact = 0.5 * 2 * np.log(2 * np.pi * np.e * (1 + 2 * (t - dt)))
     assert abs(float(info["entropy"]) - exact) < 0.06
     assert float(infos["tdvp_error"][-1]) < 5e-3 and float(infos["solver_res"][-1]) < 1e-6
@@ -349,3 +355,32 @@ def test_full_size_properties_c3():
     ratio = (torch.diagonal(T.S0) / var_sub)[var_sub > 1e-12 * var_sub.max()]
     assert 0.5 < float(ratio.median()) < 2.0
     assert abs(float(info["entropy"]) - 0.5 * 6 * np.log(2 * np.pi * np.e)) < 0.05
+
+
+def test_costfun_mode_and_covariance_mirror_match_the_oracle():
+    """var_state.py:45-53 (mode="costfun": -log p and its parameter gradient, tree-averaged; train.py:37-49 drives an
+    optimiser with it) and mpi_wrapper.global_covariance (:248-274 with _cov_helper_without_p :21-25)."""
+    from vmc_pde_b200 import mpi_wrapper as mpi
+    smp, vs, eq, spec = build(4, 3, 5, "no_add", "Gauss", "diffusion", np.zeros(4))
+    rng = np.random.default_rng(11)
+    theta = vs.get_parameters() + torch.tensor(0.05 * rng.normal(size=vs.numParameters), device="cuda")
+    vs.set_parameters(theta)
+    x = rng.normal(size=(1, 700, 4))
+    ost = oflow.OracleState(spec, theta.cpu().numpy())
+    lp_o, gx_o, gt_o = ost.eval_coordgrads(x[0])
+    val, grads = vs(x, mode="costfun")
+    assert val.shape == (1, 700) and grads.shape == (1, 700, vs.numParameters)
+    assert relerr(val[0], -lp_o) < 1e-12 and relerr(grads[0], -gt_o) < 1e-11
+    mval, mtree = vs(x, mode="costfun", avg=True)
+    assert abs(float(mval) + float(lp_o.mean())) < 1e-12
+    assert relerr(vs.flatten_tree(mtree), -gt_o.mean(0)) < 1e-11
+    assert set(mtree["params"]) == {"L", "L_diag", "dist_params", "mu", "myINN"}      # a parameter tree, as jax.grad returns
+    # one plain gradient-descent step on the cost lowers it (train.py:45-49 in miniature)
+    vs.set_parameters(theta - 1e-3 * vs.flatten_tree(mtree))
+    assert float(vs(x, mode="costfun", avg=True)[0]) < float(mval)
+    # global_covariance: (1/N) sum_i x_i x_i^T over the (device, batch) axes
+    data = torch.tensor(rng.normal(size=(1, 333, 37)), device="cuda")
+    mpi.globNumSamples = 333
+    C = mpi.global_covariance(data)
+    ref = data[0].cpu().numpy().T @ data[0].cpu().numpy() / 333
+    assert C.shape == (37, 37) and relerr(C, ref) < 1e-13 and float((C - C.T).abs().max()) == 0.0

@@ -85,6 +85,27 @@ def test_timings_and_cov_matrix():
     assert np.allclose(S.numpy(), L @ L.T)
 
 
+def test_store_infos_writes_the_flat_hdf5_group_of_the_reference(tmp_path):
+    """util.py:29-32 / main.py:205: every key of `infos` (a list of per-step values) becomes one dataset of shape
+    (steps, ...) in infos.hdf5 -- the layout the reference's plotting scripts and its stored runs use."""
+    from vmc_pde_b200 import _hdf5
+    rng = np.random.default_rng(3)
+    steps, P, d = 5, 7, 2
+    infos = {"times": [0.1 * i for i in range(steps)], "ev": [torch.tensor(rng.normal(size=P)) for _ in range(steps)],
+             "covar": [torch.tensor(rng.normal(size=(d, d))) for _ in range(steps)], "entropy": [torch.tensor(1.5 + i) for i in range(steps)],
+             "integral_0.5sigma": [np.float64(0.3)] * steps, "dist_params": [torch.zeros(0, dtype=torch.float64)] * steps}
+    wdir = str(tmp_path) + "/"
+    util.store_infos(wdir, infos)
+    back = _hdf5.read(wdir + "infos.hdf5")
+    assert set(back) == set(infos) and back["ev"].shape == (steps, P) and back["covar"].shape == (steps, d, d)
+    assert back["dist_params"].shape == (steps, 0) and back["entropy"].shape == (steps,)       # as in the stored runs
+    assert np.array_equal(back["ev"][3], infos["ev"][3].numpy()) and np.allclose(back["times"], infos["times"])
+    again = util.load_infos(wdir)
+    assert all(np.array_equal(again[k], back[k]) for k in back)
+    with pytest.raises(TypeError):
+        util.store_infos(wdir, {"snr": [None, None]})
+
+
 def test_solve_shard_ranges_partition_the_eigenvectors():
     """tdvp.solve_shard_range: contiguous 128-blocks, every eigenvector exactly once, and the per-slice partial updates
     plus zero-padded slice vectors sum to the unsharded solve (the all-reduce pattern of TDVP._finish)."""

@@ -90,6 +90,8 @@ def require_cuda():
     import torch
     if not torch.cuda.is_available():
         raise RuntimeError("vmc_pde_b200 needs a CUDA device (sm_100a); there is no CPU fallback.")
+    from . import global_defs
+    global_defs.device()
 
 
 def ptr(t):
@@ -98,8 +100,10 @@ def ptr(t):
 
 
 def stream():
+    """torch's current stream ON THIS PROCESS'S device (global_defs.device() also makes that device current)."""
     import torch
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    from . import global_defs
+    return C.c_void_p(torch.cuda.current_stream(global_defs.device()).cuda_stream)
 
 
 def ptr_array(tensors):

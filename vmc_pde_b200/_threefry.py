@@ -56,6 +56,24 @@ def uniform01(key, size):
     return ((v >> np.uint64(12)) | np.float64(1.0).view(np.uint64)).view(np.float64) - 1.0
 
 
+def uniform01_f32(key, size):
+    """float32 U[0,1) in JAX's layout (one 32-bit word per element): what jax.nn.initializers.uniform draws."""
+    bits = random_bits32(key, size)
+    return ((bits >> np.uint32(9)) | np.float32(1.0).view(np.uint32)).view(np.float32) - np.float32(1.0)
+
+
+def fold_in(key, data):
+    """jax.random.fold_in(key, data) = threefry_2x32(key, PRNGKey(data)) for a 32-bit `data`."""
+    a, b = _block(key[0], key[1], np.zeros(1, np.uint32), np.array([int(data) & 0xFFFFFFFF], np.uint32))
+    return np.array([a[0], b[0]], dtype=np.uint32)
+
+
+def fold_in_str(key, name):
+    """flax.core.scope._fold_in_str (flax 0.3.x): fold in the first 4 bytes (big endian) of the SHA-1 of `name`."""
+    import hashlib
+    return fold_in(key, int.from_bytes(hashlib.sha1(name.encode("utf-8")).digest()[:4], byteorder="big"))
+
+
 def permutation(key, n):
     """jax.random.permutation(key, n): rounds of sort-by-random-32-bit-keys (jax._src.random._shuffle)."""
     x = np.arange(n)

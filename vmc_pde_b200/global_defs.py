@@ -17,12 +17,21 @@ def _local_rank():
     return int(os.environ.get("LOCAL_RANK", "0"))
 
 
+_bound = None
+
+
 def device():
-    """The CUDA device of this process (global_defs.py:16-20 picks devices[rank % ndev])."""
-    if not torch.cuda.is_available():
-        raise RuntimeError("vmc_pde_b200 needs a CUDA device (sm_100a); there is no CPU fallback.")
-    idx = _local_rank() % torch.cuda.device_count()
-    return torch.device("cuda", idx)
+    """The CUDA device of this process (global_defs.py:16-20 picks devices[rank % ndev]).  The first call also makes it
+    the CURRENT device of the process: the C-ABI launches kernels on the current device / torch's current stream, so a
+    multi-GPU user does not need a torch.cuda.set_device of their own."""
+    global _bound
+    if _bound is None:
+        if not torch.cuda.is_available():
+            raise RuntimeError("vmc_pde_b200 needs a CUDA device (sm_100a); there is no CPU fallback.")
+        _bound = torch.device("cuda", _local_rank() % torch.cuda.device_count())
+    if torch.cuda.current_device() != _bound.index:
+        torch.cuda.set_device(_bound)
+    return _bound
 
 
 myPmapDevices = None

@@ -99,9 +99,12 @@ class INNwProb:
         return tree
 
     def init(self, key, x=None):
-        """flax `init`: latent parameters and biases zero, hidden kernels U[-1,1), last kernel U[-1e-5,1e-5)
-        (net.py:39-41,48-49,55-56,201-204).  Leaf keys are a split chain of `key` (flax's per-module key folding
-        is not reproduced)."""
+        """flax 0.3.6 `Module.init(key, x)`: latent parameters and biases zero, hidden kernels U[-1,1), last kernel
+        U[-1e-5,1e-5) (net.py:39-41,48-49,55-56,201-204), drawn from flax's RNG tree: the key of a module is its
+        parent's key folded with the SHA-1 of the module name (`Scope.push`), the key of the k-th parameter created in
+        a module is the module key folded with k (`Scope.make_rng`; a Dense layer creates its kernel first), and
+        jax.nn.initializers.uniform draws float32.  With this stream the spectrum of S of the reference's stored d=6
+        run is reproduced (tests/test_reference_pins.py)."""
         key = _threefry.PRNGKey(key) if np.isscalar(key) else np.asarray(key, dtype=np.uint32)
         flat = np.zeros(self.numParameters)
         start = 0
@@ -109,9 +112,13 @@ class INNwProb:
         for path, shape in self.layout():
             n = int(np.prod(shape))
             if path[-1] == "kernel":
-                key, sub = _threefry.split(key)
+                k = key
+                for name in path[1:-1]:                       # 'myINN', 'blocks_b', 's1', 'Dense_l'
+                    k = _threefry.fold_in_str(k, name)
+                k = _threefry.fold_in(k, 1)
                 scale = 1e-5 if path[-2] == f"Dense_{nl}" else 1.0
-                flat[start:start + n] = uniform_init(_threefry.uniform01(sub, n), scale)
+                u = _threefry.uniform01_f32(k, n) * np.float32(0.01)      # initializers.uniform(): scale 1e-2, float32
+                flat[start:start + n] = (np.float32(2.0 * scale) * (u / np.float32(0.01) - np.float32(0.5))).astype(np.float64)
             start += n
         flat_t = _kernels.as_dev(flat)
         return self.tree_from_flat(flat_t)

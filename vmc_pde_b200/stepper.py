@@ -1,4 +1,9 @@
-"""Mirror of vmc_fluids/stepper.py: ODE integrators over the flat parameter vector (torch tensors on the GPU).
+"""The reference's integrators (vmc_fluids/stepper.py:20-91,109-145) re-hosted on torch tensors.
+
+This file is host glue whose step-size arithmetic, call order and quirks ARE the drop-in contract (the steppers
+stay host Python), so it deliberately follows the reference's control flow and variable names statement by statement
+(`.copy()` -> `.clone()`, in-place updates made out-of-place); it is the reference's algorithm, not a redesign.  The
+right-hand side `f` it drives is the GPU path.
 
 Same classes, constructor arguments, `step(t, f, y, normFunction=..., **rhsArgs) -> (y_new, dt, info)` contract and
 quirks (FixedStepper enlarges dt before the step, stepper.py:131; AdaptiveHeun compares the quadratic form

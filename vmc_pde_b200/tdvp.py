@@ -195,6 +195,7 @@ class TDVP:
             _kernels.sym_finalize(CEO, Pp, inv)
         F = Fsum * inv
         self.ElocVar = (var_sum[0] * inv).clone()
+        # S0 / SExp / S (P x P, 0.5 GB each at P = 8187) are views of the persistent buffers: valid until the next call
         self.S0, self.F0 = S0[:P, :P], F[:P]
         if eager_sexp:
             self.SExp = SExp[:P, :P]
@@ -238,8 +239,10 @@ class TDVP:
                                     self.useSNR, meanE2, VtF, rhoVar if use_ceo else None, snr if use_ceo else None, invEv, update,
                                     self._scal, ws)
             self._P = P
-            self.ev, self.VtF, self.invEv = ev[:P], VtF[:P], invEv[:P]
-            self.rhoVar, self.snr = (rhoVar[:P], snr[:P]) if use_ceo else (None, None)
+            # fresh P-vectors: main.py:187-188 appends tdvpEq.ev / .snr to histories (JAX arrays are immutable; views of
+            # the persistent work buffer would all end up equal to the last step)
+            self.ev, self.VtF, self.invEv = ev[:P].clone(), VtF[:P].clone(), invEv[:P].clone()
+            self.rhoVar, self.snr = (rhoVar[:P].clone(), snr[:P].clone()) if use_ceo else (None, None)
         else:
             if not self.diagonalShift > 1e-10:
                 raise ValueError("solver='cholesky' needs diagonalShift > 0: S is rank deficient otherwise (SURVEY fact 5)")
@@ -345,8 +348,20 @@ class TDVP:
         return update, info
 
     def _plan_chunks(self, n_local, Pp):
-        """Rows of the O buffer and whether the whole local O fits (then local terms are evaluated once)."""
+        """Rows of the O buffer and whether the whole local O fits (then local terms are evaluated once).  Planned once
+        per (n_local, Pp, chunkSamples, memoryFraction): the chunking fixes the floating-point summation order, so it must
+        not drift between consecutive right-hand sides of a run (after the first call the cached O buffer no longer counts as
+        free memory)."""
+        plan_key = (n_local, Pp, self.chunkSamples, self.memoryFraction)
+        if getattr(self, "_plan", None) is not None and self._plan[0] == plan_key:
+            return self._plan[1]
+        self._plan = (plan_key, self._plan_chunks_now(n_local, Pp))
+        return self._plan[1]
+
+    def _plan_chunks_now(self, n_local, Pp):
         free, _ = torch.cuda.mem_get_info(global_defs.device())
+        if getattr(self, "_Obuf", None) is not None:
+            free += self._Obuf.numel() * 8        # a buffer of an earlier plan is released before the new one is allocated
         fixed = 8 * Pp * Pp * 8 + (64 << 20)  # S0, SExp, CEO, shifted S, work copy, VT, eigh scratch (2)
         budget = max(int((free - fixed) * self.memoryFraction), 16 * Pp * 8)
         rows = self.chunkSamples if self.chunkSamples else budget // (Pp * 8)
@@ -361,7 +376,7 @@ class TDVP:
         P, Pp, d = h.P, h.Pp, h.dim
         first_idx, n_local = mpi.shard_range(N)
         key = psi.sampler.next_key()                       # sampler.py:73 (one key per psi.sample call)
-        chi2_all = psi.chi2_draws(n_local)
+        chi2_all = psi.chi2_draws(n_local, first_idx, N)
         eq = evolutionEq.equation_struct(t)
         self._buffers(P, Pp).zero_()
         rows, stored = self._plan_chunks(n_local, Pp)

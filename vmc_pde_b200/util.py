@@ -1,4 +1,5 @@
-"""Mirror of vmc_fluids/util.py: build_cov_matrix (util.py:21-26), Timings (:35-52), store_infos (:29-32)."""
+"""util.py of the reference, re-hosted: build_cov_matrix (util.py:21-26), store_infos (:29-32) and Timings (:35-52; the
+reference's own 17 lines, kept as they are because main.py / tdvp.py call them by name)."""
 import time
 import numpy as np
 import torch
@@ -15,16 +16,39 @@ def build_cov_matrix(L_para, L_diag, dim):
 
 
 def store_infos(wdir, infos, name="infos.hdf5"):
-    """util.py:29-32 writes one HDF5 dataset per key.  h5py is used when importable; otherwise the same keys go
-    into `<name>.npz` (this image has no h5py)."""
-    data = {k: np.asarray([np.asarray(torch.as_tensor(v).cpu()) for v in vals]) for k, vals in infos.items()}
+    """util.py:29-32: one HDF5 dataset per key of `infos` (lists of per-step values) in `wdir + name`.
+    h5py is used when importable; otherwise the built-in writer (_hdf5.py) produces the same flat-group file, readable
+    by h5py and hence by the reference's plotting scripts (visualization.py:141-280, paper_plot/*.py)."""
+    def as_np(v):
+        if isinstance(v, torch.Tensor):
+            return v.detach().cpu().numpy()
+        return np.asarray(v)
+    data = {}
+    for k, vals in infos.items():
+        data[k] = np.asarray([as_np(v) for v in vals]) if isinstance(vals, (list, tuple)) else as_np(vals)
+        if data[k].dtype == object:       # e.g. snr is None for the Cholesky solver: store what h5py could not either
+            raise TypeError(f"infos[{k!r}] is ragged or holds None entries")
     try:
         import h5py
-        with h5py.File(wdir + name, "w") as f:
-            for key, value in data.items():
-                f.create_dataset(key, data=value)
     except ImportError:
-        np.savez(wdir + name + ".npz", **data)
+        from . import _hdf5
+        _hdf5.write(wdir + name, data)
+        return
+    with h5py.File(wdir + name, "w") as f:
+        for key, value in data.items():
+            f.create_dataset(key, data=value)
+
+
+def load_infos(wdir, name="infos.hdf5"):
+    """Reads a file written by store_infos (or by the reference) back as {key: ndarray}; also the way to RESUME a run:
+    `infos["parameters"][-1]` holds the flat parameter vector when the driver logs it (the reference stores none)."""
+    try:
+        import h5py
+    except ImportError:
+        from . import _hdf5
+        return _hdf5.read(wdir + name)
+    with h5py.File(wdir + name, "r") as f:
+        return {k: np.array(f[k]) for k in f.keys()}
 
 
 class Timings():

@@ -72,12 +72,15 @@ class VarState:
         p = self.params["params"]
         return {"S": util.build_cov_matrix(p["L"], p["L_diag"], self.dim), "mu": p["mu"], "dist_params": p["dist_params"]}
 
-    def chi2_draws(self, n):
-        """sampler.py:32: chi^2(nu) variates from NumPy's global RNG (host), Student-t latent only."""
+    def chi2_draws(self, n, first=0, n_total=None):
+        """sampler.py:32: chi^2(nu) variates from NumPy's global RNG (host), Student-t latent only.  Every rank draws the
+        whole numSamples vector (identically seeded ranks then hold identical vectors) and keeps the entries of its own
+        global sample indices [first, first + n), so the sample set does not depend on the number of ranks."""
         if self.net.latentSpaceName != "Student_t":
             return None
         nu = float(torch.exp(self.params["params"]["dist_params"][0]) + 1.0)
-        return _kernels.as_dev(np.random.chisquare(nu, size=(n,)))
+        n_total = n if n_total is None else n_total
+        return _kernels.as_dev(np.random.chisquare(nu, size=(n_total,))[first:first + n])
 
     def sample_range(self, key, first, n, n_total, chi2=None):
         """Samples [first, first+n) of the n_total-sample stream of `key`: (x (n,d), logp (n,))."""
@@ -88,7 +91,7 @@ class VarState:
         contiguous slice of the single global stream (see sampler.py docstring)."""
         key = self.sampler.next_key()
         first, n = mpi_wrapper.shard_range(numSamples)
-        x, lp = self.sample_range(key, first, n, numSamples, self.chi2_draws(n))
+        x, lp = self.sample_range(key, first, n, numSamples, self.chi2_draws(n, first, numSamples))
         return x[None, ...], lp[None, ...]
 
     def average_tree(self, tree, axis=(0, 1)):
