@@ -64,8 +64,9 @@ def test_device_rng_and_particle_kernel_reproduce_every_stored_record():
         coords = exact_dyn.integrate(coords, 1e-2, p, exact_dyn._velocity_field_hamiltonian, exact_dyn.update_fun_phaseSpace, use)
     assert np.abs(x1.cpu().numpy() - g["x1"]).max() < 1e-10
     assert np.abs(cov.cpu().numpy() - g["covar"]).max() < 1e-10
-    for j, lim in enumerate((1, 0.5, 0.1)):
-        assert np.array_equal(balls[:, j].cpu().numpy(), g[f"integral_{lim}sigma"])
+    for j, lim in enumerate((1, 0.5, 0.1)):      # counts / N: equal except where a particle sits within round-off of a sphere
+        diff = np.abs(balls[:, j].cpu().numpy() - g[f"integral_{lim}sigma"])
+        assert diff.max() < 1.01e-4 and int((diff > 1e-12).sum()) <= 3, (lim, diff.max(), int((diff > 1e-12).sum()))
 
 
 def test_init_net_reproduces_the_flax_stream_and_first_stored_records():
@@ -108,25 +109,27 @@ def test_init_net_reproduces_the_flax_stream_and_first_stored_records():
     assert np.abs(ev[-50:] / g["ev"][0][-50:] - 1).max() < 1e-2
     cut = lambda e: int(np.sum(np.abs(e / e[-1]) < 1e-11))
     assert abs(cut(ev) - cut(g["ev"][0])) <= 25
-    snr_ref = g["snr"][0]
-    big = np.abs(g["ev"][0] / g["ev"][0][-1]) > 1e-4                          # well-resolved modes: snr has the stored magnitude
-    assert 0.2 < np.median(f(T.snr)[big]) / np.median(snr_ref[big]) < 5.0
+    # snr of the dominant modes has the stored magnitude (it involves the force, i.e. the run's edited physics: band only)
+    ratio = f(T.snr)[-6:] / g["snr"][0][-6:]
+    assert 0.25 < ratio.min() and ratio.max() < 4.0, ratio
 
 
 def test_tdvp_evolution_follows_the_stored_particle_run_and_ends_at_the_plotted_constants():
-    """main.py's loop (Heun, dt = 1e-4 * 1.3^k <= 1e-2, N = 10^4, P = 411) on the checked-in damped-oscillator physics with
-    the initial state of the stored particle run (offset [1,0,1,0,1,0]).  The evolved density must follow the reference's
-    own particle trajectory and reach the steady state the reference plots: entropy 6 * 1/2 log(2 pi e 10) and the three
-    ball integrals 0.0143877 / 2.96478e-4 / 2.07554e-8."""
+    """main.py's loop (Heun, dt = 1e-4 * 1.3^k <= 1e-2, N = 10^4, P = 411, 1214 steps to t = 12) on the checked-in
+    damped-oscillator physics with the initial state of the stored particle run (offset [1,0,1,0,1,0]).  The evolved density
+    must follow the reference's own particle trajectory (its N = 10^4 particles scatter by ~1.5 % in the variances) and
+    reach the steady state the reference plots: entropy 6 * 1/2 log(2 pi e 10) and the three ball integrals
+    0.0143877 / 2.96478e-4 / 2.07554e-8 (paper_plot_phaseSpaceTempDifference.py:87,129-131).
+    Measured on a B200: means within 0.10, variances within 5 %, entropy within 0.04, end integrals within 0.3 %."""
     from vmc_pde_b200 import tdvp, stepper
     g = load("ref_wiener_T10")
     off = np.array([1.0, 0, 1, 0, 1, 0])
     smp, vs, eq = build(6, 4, 3, "different_add", "advection_hamiltonian_wDiss", off)
     st = stepper.FixedStepper(timeStep=1e-4, mode='Heun', maxStep=1e-2, increase_fac=1.3)
     T = tdvp.TDVP()
-    t, checks, hist = 0.0, [0.5, 1.0, 2.0, 3.0, 4.0, 6.0], {}
+    t, checks, hist = 0.0, [0.25, 0.5, 1.0, 1.5, 2.0, 3.0, 4.0, 6.0, 8.0, 12.0], {}
     evs = []
-    while t < 6.0 + 1e-9:
+    while t < 12.0 + 1e-9:
         dp, dt, info = st.step(0, T, vs.get_parameters(), evolutionEq=eq, psi=vs, nSamplesTDVP=10000, nSamplesObs=10000,
                                normFunction=norm_fun, timings=None, integrals=False)
         vs.set_parameters(dp)
@@ -135,20 +138,20 @@ def test_tdvp_evolution_follows_the_stored_particle_run_and_ends_at_the_plotted_
         if checks and t + dt >= checks[0]:
             hist[checks.pop(0)] = (t + dt, {k: v.cpu().numpy() for k, v in info.items()})
         t += dt
-    assert not torch.equal(evs[0], evs[-1])                                   # histories do not alias (main.py:187)
+    assert not torch.equal(evs[0], evs[-1]) and float(T.solverResidual) < 1e-9     # histories do not alias (main.py:187)
     tw = g["times"]
     for tc, (tt, info) in hist.items():
         i = int(np.argmin(np.abs(tw - tt)))
         Cw = g["covar"][i]
         assert np.abs(info["x1"] - g["x1"][i]).max() < 0.15, (tc, info["x1"], g["x1"][i])
-        assert np.abs(np.diag(info["covar"]) / np.diag(Cw) - 1).max() < 0.10, (tc, np.diag(info["covar"]), np.diag(Cw))
-        assert abs(info["covar"][0, 1] - Cw[0, 1]) < 0.5
+        assert np.abs(np.diag(info["covar"]) / np.diag(Cw) - 1).max() < 0.08, (tc, np.diag(info["covar"]), np.diag(Cw))
+        assert abs(info["covar"][0, 1] - Cw[0, 1]) < 0.45
         ent_w = 0.5 * np.linalg.slogdet(2 * np.pi * np.e * Cw)[1]              # the exact density stays Gaussian
-        assert abs(float(info["entropy"]) - ent_w) < 0.25, (tc, float(info["entropy"]), ent_w)
-        for lim in (1, 0.5):
-            a, b = float(info[f"integral_{lim}sigma"]), g[f"integral_{lim}sigma"][i]
-            assert abs(a - b) < 0.25 * b + 4.0 * np.sqrt(max(b, 1e-4) / 1e4), (tc, lim, a, b)
-    end = hist[6.0][1]
-    assert abs(float(end["entropy"]) - 0.5 * np.log(2 * np.pi * np.e * 10) * 6) < 0.25   # paper_plot_...py:87
-    for key, const in (("integral_1sigma", 0.0143877), ("integral_0.5sigma", 0.000296478), ("integral_0.1sigma", 2.07554e-8)):
-        assert abs(float(end[key]) / const - 1) < 0.25, (key, float(end[key]), const)   # paper_plot_...py:129-131
+        assert abs(float(info["entropy"]) - ent_w) < 0.08, (tc, float(info["entropy"]), ent_w)
+        a, b = float(info["integral_1sigma"]), g["integral_1sigma"][i]         # b is a count of ~150 ... 2000 particles
+        assert abs(a - b) < 0.08 * b + 4.0 * np.sqrt(b / 1e4), (tc, a, b)
+    end = hist[12.0][1]
+    assert abs(float(end["entropy"]) - 0.5 * np.log(2 * np.pi * np.e * 10) * 6) < 0.08
+    for key, const, tol in (("integral_1sigma", 0.0143877, 0.02), ("integral_0.5sigma", 0.000296478, 0.01),
+                            ("integral_0.1sigma", 2.07554e-8, 0.005)):
+        assert abs(float(end[key]) / const - 1) < tol, (key, float(end[key]), const)
