@@ -184,6 +184,19 @@ int vmcpde_eigh(double* S, int32_t n, int32_t ld, double* ev, double* VT, void* 
  * writes every row. */
 int vmcpde_eigh_cols(double* S, int32_t n, int32_t ld, double* ev, double* VT, int32_t col0, int32_t ncols,
                      void* workspace, size_t workspace_bytes, vmcpde_stream stream);
+/* The same eigensolver in two calls, for a multi-GPU solve in which ONE rank runs the serial stages while the others
+ * still build Gram matrices (np.linalg.eigh of tdvp.py:61-64 split at its only parallel seam): vmcpde_eigh_factor =
+ * scaling + tridiagonalisation + divide & conquer; it leaves the reflectors in S, tau[n], Z^T (rows x ld with rows = n
+ * rounded up to 128; row k = eigenvector k of the tridiagonal matrix) and ev[n] in caller-owned buffers that can be
+ * broadcast.  vmcpde_eigh_backtransform applies the reflectors to the 128-aligned eigenvector slice [col0, col0+ncols)
+ * (ncols <= 0: all) and writes rows col0.. of VT (VT must not alias the inputs).  factor + backtransform of all
+ * columns == vmcpde_eigh bit for bit.  Blocked path only (n >= 384, ld a multiple of 128): VMCPDE_EUNSUPPORTED otherwise.
+ * Workspace: vmcpde_eigh_workspace_bytes for both. */
+int vmcpde_eigh_factor(double* S, int32_t n, int32_t ld, double* ev, double* ZT, double* tau, void* workspace,
+                       size_t workspace_bytes, vmcpde_stream stream);
+int vmcpde_eigh_backtransform(const double* reflectors, const double* tau, const double* ZT, int32_t n, int32_t ld,
+                              double* VT, int32_t col0, int32_t ncols, void* workspace, size_t workspace_bytes,
+                              vmcpde_stream stream);
 /* number of kernel launches one vmcpde_eigh(n, ld) call issues */
 int vmcpde_eigh_launch_count(int32_t n, int32_t ld, int32_t* count);
 /* Everything after eigh in TDVP.transform_to_eigenbasis / TDVP.solve (tdvp.py:66-94): VtF = V^T F;

@@ -315,6 +315,32 @@ def test_eigh_at_benchmark_sizes_against_the_library_solver(L, n):
     assert int((ev[:n].abs() < 1e-11 * nrm).sum()) >= n // 2 - 8   # the null space is resolved as such
 
 
+def test_eigh_two_call_form_equals_the_single_call(L):
+    """vmcpde_eigh_factor + vmcpde_eigh_backtransform (the seam of the pipelined multi-GPU solve) == vmcpde_eigh bit for bit,
+    slice by slice, also when the caller's Z^T / VT buffers hold garbage on entry; the unblocked sizes refuse."""
+    from vmc_pde_b200 import _lib
+    rng = np.random.default_rng(21)
+    f64 = torch.float64
+    for n in (700, 2053):
+        A = rng.normal(size=(n + 50, n)) * 10.0 ** (-5.0 * np.arange(n) / n); S_np = A.T @ A / (n + 50)
+        ev0, V0 = _eigh(L, S_np)
+        ld = L.vmcpde_padded_params(n)
+        S = torch.zeros(ld, ld, device=dev(), dtype=f64); S[:n, :n] = torch.tensor(S_np, device=dev())
+        ev = torch.zeros(ld, device=dev(), dtype=f64); tau = torch.zeros(ld, device=dev(), dtype=f64)
+        ZT = torch.full((ld, ld), float("nan"), device=dev(), dtype=f64)
+        VT = torch.full((ld, ld), 7.0, device=dev(), dtype=f64)
+        nb = C.c_size_t(0); _lib.check(L.vmcpde_eigh_workspace_bytes(n, ld, C.byref(nb)))
+        ws = torch.empty(nb.value, device=dev(), dtype=torch.uint8)
+        _lib.check(L.vmcpde_eigh_factor(_lib.ptr(S), n, ld, _lib.ptr(ev), _lib.ptr(ZT), _lib.ptr(tau), _lib.ptr(ws), nb.value, _lib.stream()))
+        ws.fill_(255)                                            # the factors live in caller buffers, not in the workspace
+        for col0, ncols in ((0, 256), (256, ld - 256)):
+            _lib.check(L.vmcpde_eigh_backtransform(_lib.ptr(S), _lib.ptr(tau), _lib.ptr(ZT), n, ld, _lib.ptr(VT), col0, ncols,
+                                                   _lib.ptr(ws), nb.value, _lib.stream()))
+        assert np.array_equal(ev[:n].cpu().numpy(), ev0) and np.array_equal(VT[:n, :n].cpu().numpy().T, V0)
+    S = torch.eye(200, device=dev(), dtype=f64)
+    assert L.vmcpde_eigh_factor(_lib.ptr(S), 200, 200, _lib.ptr(ev), _lib.ptr(ZT), _lib.ptr(tau), _lib.ptr(ws), nb.value, _lib.stream()) == 2
+
+
 def test_eigh_is_run_to_run_deterministic(L):
     """Fixed-order reductions and tagged messages: two runs on the same matrix agree bit for bit (blocked path, both
     mat-vec modes), and so do the replicated solves of a multi-GPU run."""

@@ -132,6 +132,27 @@ def test_solve_shard_ranges_partition_the_eigenvectors():
     assert np.allclose(acc, full, rtol=1e-12, atol=1e-12) and np.allclose(vt[:P], V.T @ F)
 
 
+def test_sample_partition_of_the_pipelined_solve():
+    """TDVP.sample_partition: contiguous, complete, deterministic; equal shards unless the solve is pipelined, then the
+    solver rank's share shrinks with the cost of the serial eigensolver stages (none at C3 on 4 and 8 ranks)."""
+    from vmc_pde_b200.tdvp import TDVP, solver_seconds
+    T = TDVP()
+    for N, R, P in ((2 ** 18, 1, 8187), (2 ** 18, 2, 8187), (2 ** 18, 4, 8187), (2 ** 18, 8, 8187), (2 ** 20, 8, 16385), (10007, 3, 2053), (1000, 2, 37)):
+        part = T.sample_partition(N, R, P)
+        assert len(part) == R and part[0][0] == 0 and sum(n for _, n in part) == N
+        assert all(part[i][0] + part[i][1] == part[i + 1][0] for i in range(R - 1)) and part == T.sample_partition(N, R, P)
+        if R > 1 and P >= 384:
+            others = [n for r, (_, n) in enumerate(part) if r != 0]
+            assert part[0][1] <= min(others) and max(others) - min(others) <= 1 and part[0][1] % 16 == 0
+    assert [n for _, n in T.sample_partition(1000, 2, 37)] == [500, 500]                       # unblocked solver: equal shards
+    assert T.sample_partition(2 ** 18, 8, 8187)[0][1] == 0 and T.sample_partition(2 ** 18, 4, 8187)[0][1] < 2 ** 18 // 16
+    n0 = T.sample_partition(2 ** 18, 2, 8187)[0][1]
+    assert 0.25 * 2 ** 18 < n0 < 0.45 * 2 ** 18
+    assert [n for _, n in TDVP(pipelineSolve=False).sample_partition(2 ** 18, 4, 8187)] == [2 ** 16] * 4
+    assert [n for _, n in TDVP(solverShare=0.5).sample_partition(2 ** 18, 4, 8187)][0] == 2 ** 15
+    assert solver_seconds(8187) == pytest.approx(0.33) and solver_seconds(4096) < solver_seconds(5000) < solver_seconds(8187)
+
+
 def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 

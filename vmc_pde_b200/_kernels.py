@@ -252,6 +252,20 @@ def eigh_cols(A_destroyed, n, ld, ev, VT, col0, ncols, ws):
                                             int(ncols), _lib.ptr(ws), ws.numel(), _lib.stream()))
 
 
+def eigh_factor(A_destroyed, n, ld, ev, ZT, tau, ws):
+    """Serial stages of the eigensolver (scaling, tridiagonalisation, divide & conquer); reflectors stay in A."""
+    _count(eigh_launch_count(n, ld))
+    _lib.check(_lib.load().vmcpde_eigh_factor(_lib.ptr(A_destroyed), int(n), int(ld), _lib.ptr(ev), _lib.ptr(ZT), _lib.ptr(tau),
+                                              _lib.ptr(ws), ws.numel(), _lib.stream()))
+
+
+def eigh_backtransform(reflectors, tau, ZT, n, ld, VT, col0, ncols, ws):
+    """Back-transformation of the eigenvector slice [col0, col0 + ncols) (rows of VT) from broadcastable factors."""
+    _count(8)
+    _lib.check(_lib.load().vmcpde_eigh_backtransform(_lib.ptr(reflectors), _lib.ptr(tau), _lib.ptr(ZT), int(n), int(ld), _lib.ptr(VT),
+                                                     int(col0), int(ncols), _lib.ptr(ws), ws.numel(), _lib.stream()))
+
+
 def solve_tail_range(ev, VT, n, ld, F, CEO, n_glob, svdTol, snrTol, useSNR, row0, nrows, VtF, rhoVar, snr, invEv,
                      update_partial, ws):
     _count(6 if CEO is not None else 3)

@@ -44,6 +44,8 @@ SIGNATURES = {
     "vmcpde_eigh_workspace_bytes": (C.c_int, [_i32, _i32, C.POINTER(C.c_size_t)]),
     "vmcpde_eigh": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, C.c_size_t, _vp]),
     "vmcpde_eigh_cols": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _i32, _i32, _vp, C.c_size_t, _vp]),
+    "vmcpde_eigh_factor": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "vmcpde_eigh_backtransform": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _i32, _i32, _vp, C.c_size_t, _vp]),
     "vmcpde_solve_tail_range": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _dbl, _dbl, _dbl, _i32, _i32, _i32,
                                           _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "vmcpde_eigh_launch_count": (C.c_int, [_i32, _i32, C.POINTER(_i32)]),

@@ -689,52 +689,67 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_eigh_launch_count(i
   return 0;
 }
 
-// S (n x n, leading dimension ld, full symmetric) is destroyed.  ev[n] ascending; VT row k = eigenvector k.
-// Replaces np.linalg.eigh at tdvp.py:61-64.
-static int eigh_impl(double* S, int32_t n, int32_t ld, double* ev, double* VT, int32_t col0, int32_t ncols, void* workspace,
-                     size_t workspace_bytes, vmcpde_stream stream) {
-  VMC_REQUIRE(S && ev && VT && workspace, "vmcpde_eigh: null pointer");
+// Workspace layout shared by the stages of the eigensolver (same carving order for every entry point, so a workspace
+// of vmcpde_eigh_workspace_bytes serves any of them).
+struct EighWs {
+  bool blocked;
+  size_t rows, tri_bytes, bt_bytes;
+  double *QTb, *U, *d, *e, *tau, *p, *p2, *sc;
+  void *tri_scratch, *bt_scratch;
+  DcBuf b;
+};
+
+static int eigh_layout(EighWs& w, int32_t n, int32_t ld, void* workspace, size_t workspace_bytes) {
+  VMC_REQUIRE(workspace, "vmcpde_eigh: null pointer");
   VMC_REQUIRE(n >= 1 && ld >= n, "vmcpde_eigh: bad dimensions");
   size_t need = 0;
   vmcpde_eigh_workspace_bytes(n, ld, &need);
   VMC_REQUIRE(workspace_bytes >= need, "vmcpde_eigh: workspace too small");
   VMC_REQUIRE(n <= 25 * 1024, "vmcpde_eigh: n > 25600 not supported in this release");
-  cudaStream_t s = (cudaStream_t)stream;
   uint8_t* wp = (uint8_t*)workspace;
-  auto take = [&](size_t bytes) { void* p = wp; wp += align_up(bytes, 256); return p; };
-  const bool blocked = blocked_eigh_supported(n, ld);
-  const size_t rows = blocked ? (size_t)(n + 127) / 128 * 128 : (size_t)n;
-  double* QTb = (double*)take(rows * ld * 8);
-  double* U = (double*)take(rows * ld * 8);
-  const size_t tri_bytes = blocked ? blocked_tridiag_scratch_bytes(n, ld) : 0;
-  const size_t bt_bytes = blocked ? blocked_backtransform_scratch_bytes(n, ld) : 0;
-  void* tri_scratch = blocked ? take(tri_bytes) : nullptr;
-  void* bt_scratch = blocked ? take(bt_bytes) : nullptr;
+  auto take = [&](size_t bytes) { void* q = wp; wp += align_up(bytes, 256); return q; };
+  w.blocked = blocked_eigh_supported(n, ld);
+  w.rows = w.blocked ? (size_t)(n + 127) / 128 * 128 : (size_t)n;
+  w.QTb = (double*)take(w.rows * ld * 8);
+  w.U = (double*)take(w.rows * ld * 8);
+  w.tri_bytes = w.blocked ? blocked_tridiag_scratch_bytes(n, ld) : 0;
+  w.bt_bytes = w.blocked ? blocked_backtransform_scratch_bytes(n, ld) : 0;
+  w.tri_scratch = w.blocked ? take(w.tri_bytes) : nullptr;
+  w.bt_scratch = w.blocked ? take(w.bt_bytes) : nullptr;
   auto dvec = [&]() { return (double*)take((size_t)(n + 8) * 8); };
   auto ivec = [&]() { return (int*)take((size_t)(n + 8) * 4); };
-  double *d = dvec(), *e = dvec(), *tau = dvec(), *p = dvec(), *p2 = dvec();
-  DcBuf b{};
-  b.n = n; b.ld = ld; b.e = e;
+  w.d = dvec(); w.e = dvec(); w.tau = dvec(); w.p = dvec(); w.p2 = dvec();
+  DcBuf& b = w.b;
+  b = DcBuf{};
+  b.n = n; b.ld = ld; b.e = w.e;
   b.lam = dvec(); b.lam_new = dvec();
   b.z = dvec(); b.dl = dvec(); b.w = dvec(); b.w2 = dvec(); b.dfv = dvec(); b.tau = dvec(); b.what = dvec();
   b.vals = dvec(); b.norm = dvec(); b.rho = dvec();
   b.order = ivec(); b.nd = ivec(); b.dfi = ivec(); b.org = ivec(); b.pos = ivec(); b.k = ivec(); b.nrot = ivec();
   b.rots = (DcRot*)take((size_t)(n + 8) * sizeof(DcRot));
-  b.QT = VT; b.QT_new = QTb; b.U = U;
+  b.QT_new = w.QTb; b.U = w.U;
+  w.sc = dvec();
+  return 0;
+}
 
-  const bool timing = getenv("VMCPDE_EIGH_TIMING") != nullptr;
-  cudaEvent_t evt[4];
-  if (timing) { for (auto& e_ : evt) cudaEventCreate(&e_); cudaEventRecord(evt[0], s); }
+// Stages 0-2: scaling, tridiagonalisation (S is overwritten by the reflectors, w.tau), divide & conquer.  `QT0` is the first
+// of the two ping-pong buffers of the divide & conquer; on return w.b.QT holds Z^T (eigenvectors of the tridiagonal matrix as
+// rows) and is either QT0 or w.QTb.
+static int eigh_factor_impl(EighWs& w, double* S, int32_t n, int32_t ld, double* ev, double* QT0, cudaStream_t s,
+                            cudaEvent_t* evt) {
+  DcBuf& b = w.b;
+  b.QT = QT0;
+  const bool blocked = w.blocked;
+  double *d = w.d, *e = w.e, *tau = w.tau, *p = w.p, *p2 = w.p2, *sc = w.sc;
   // ---- stage 0
   const int sms = num_sms();
-  double* sc = dvec();
   VMC_CUDA_CHECK(cudaMemsetAsync(sc, 0, 3 * sizeof(double), s));
   absmax_kernel<<<sms * 8, 256, 0, s>>>(S, n, ld, sc);
   scale_factor_kernel<<<1, 1, 0, s>>>(sc);
   scale_by_kernel<<<sms * 8, 256, 0, s>>>(S, (size_t)n * ld, sc + 1);
   // ---- stage 1
   if (blocked) {
-    if (int rc = tridiag_blocked(S, n, ld, d, e, tau, tri_scratch, tri_bytes, s)) return rc;
+    if (int rc = tridiag_blocked(S, n, ld, d, e, tau, w.tri_scratch, w.tri_bytes, s)) return rc;
   } else if (n >= 3) {
     double* wbuf[2] = {p, p2};
     {  // prologue: reflector 0 and its w
@@ -761,10 +776,10 @@ static int eigh_impl(double* S, int32_t n, int32_t ld, double* ev, double* VT, i
   if (!blocked) tridiag_tail_kernel<<<1, 32, 0, s>>>(S, ld, n, d, e);
   VMC_LAUNCH_CHECK("tridiagonalisation");
 
-  if (timing) cudaEventRecord(evt[1], s);
+  if (evt) cudaEventRecord(evt[1], s);
   // ---- stage 2 (the ping buffer must be zero outside the diagonal blocks written level by level)
-  VMC_CUDA_CHECK(cudaMemsetAsync(QTb, 0, rows * ld * 8, s));
-  if (rows > (size_t)n) VMC_CUDA_CHECK(cudaMemsetAsync(VT + (size_t)n * ld, 0, (rows - n) * ld * 8, s));
+  VMC_CUDA_CHECK(cudaMemsetAsync(w.QTb, 0, w.rows * ld * 8, s));
+  if (w.rows > (size_t)n) VMC_CUDA_CHECK(cudaMemsetAsync(QT0 + (size_t)n * ld, 0, (w.rows - n) * ld * 8, s));
   dc_init_kernel<<<sms * 4, 256, 0, s>>>(b, d);
   const int D = dc_tree_depth(n);
   static bool attr = false;
@@ -794,37 +809,57 @@ static int eigh_impl(double* S, int32_t n, int32_t ld, double* ev, double* VT, i
   }
   VMC_CUDA_CHECK(cudaMemcpyAsync(ev, b.lam, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
   scale_by_kernel<<<max(1, min(sms, (n + 255) / 256)), 256, 0, s>>>(ev, (size_t)n, sc + 2);
+  return 0;
+}
 
-  if (timing) cudaEventRecord(evt[2], s);
-  // ---- stage 3 (out of place: ZT = b.QT -> VT; if they alias, stage through the other buffer)
-  const double* ZT = b.QT;
-  if (blocked) {
-    // Zn = ZT^T lives in U, the reflector transpose in the free ping buffer; VT may alias either source
+// Stage 3: V = Q Z for the eigenvectors [col0, col0 + ncols).  A holds the reflectors (read only), ZT the rows of Z^T,
+// AT is a free rows x ld buffer for the masked reflector transpose; VT may alias ZT or AT on the blocked path.
+static int eigh_back_impl(EighWs& w, double* A, const double* tau, int32_t n, int32_t ld, const double* ZT, double* AT,
+                          double* VT, int32_t col0, int32_t ncols, cudaStream_t s) {
+  if (w.blocked) {
     const int np = (n + 127) / 128 * 128;
     if (ncols <= 0) { col0 = 0; ncols = np; }
-    if (int rc = backtransform_blocked(S, tau, n, ld, ZT, U, b.QT_new, bt_scratch, bt_bytes, VT, col0, ncols, s)) return rc;
-  } else if (ZT == VT) {
-    VMC_CUDA_CHECK(cudaMemcpyAsync(QTb, VT, (size_t)n * ld * 8, cudaMemcpyDeviceToDevice, s));
-    ZT = QTb;
-  }
-  if (!blocked) {
+    if (int rc = backtransform_blocked(A, tau, n, ld, ZT, w.U, AT, w.bt_scratch, w.bt_bytes, VT, col0, ncols, s)) return rc;
+  } else {
+    if (ZT == VT) {
+      VMC_CUDA_CHECK(cudaMemcpyAsync(AT, VT, (size_t)n * ld * 8, cudaMemcpyDeviceToDevice, s));
+      ZT = AT;
+    }
     const int cpt = (n + 1023) / 1024;
     int rc = 0;
-    if (cpt <= 1) rc = launch_backtransform<1, 8>(ZT, VT, S, tau, n, ld, s);
-    else if (cpt <= 2) rc = launch_backtransform<2, 8>(ZT, VT, S, tau, n, ld, s);
-    else if (cpt <= 4) rc = launch_backtransform<4, 4>(ZT, VT, S, tau, n, ld, s);
-    else if (cpt <= 8) rc = launch_backtransform<8, 2>(ZT, VT, S, tau, n, ld, s);
+    if (cpt <= 1) rc = launch_backtransform<1, 8>(ZT, VT, A, tau, n, ld, s);
+    else if (cpt <= 2) rc = launch_backtransform<2, 8>(ZT, VT, A, tau, n, ld, s);
+    else if (cpt <= 4) rc = launch_backtransform<4, 4>(ZT, VT, A, tau, n, ld, s);
+    else if (cpt <= 8) rc = launch_backtransform<8, 2>(ZT, VT, A, tau, n, ld, s);
     else {
       int rpc = (int)((200 * 1024 - 1024) / ((size_t)n * 8));
       if (rpc > 4) rpc = 4;
       if (rpc < 1) rpc = 1;
       const size_t bsm = (size_t)rpc * n * 8 + 2 * 8 * 4 * 8;
       VMC_CUDA_CHECK(cudaFuncSetAttribute(backtransform_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-      backtransform_smem_kernel<<<(n + rpc - 1) / rpc, 256, bsm, s>>>(ZT, VT, S, tau, n, ld, rpc);
+      backtransform_smem_kernel<<<(n + rpc - 1) / rpc, 256, bsm, s>>>(ZT, VT, A, tau, n, ld, rpc);
     }
     if (rc) return rc;
   }
   VMC_LAUNCH_CHECK("backtransform_kernel");
+  return 0;
+}
+
+// S (n x n, leading dimension ld, full symmetric) is destroyed.  ev[n] ascending; VT row k = eigenvector k.
+// Replaces np.linalg.eigh at tdvp.py:61-64.
+static int eigh_impl(double* S, int32_t n, int32_t ld, double* ev, double* VT, int32_t col0, int32_t ncols, void* workspace,
+                     size_t workspace_bytes, vmcpde_stream stream) {
+  VMC_REQUIRE(S && ev && VT && workspace, "vmcpde_eigh: null pointer");
+  EighWs w;
+  if (int rc = eigh_layout(w, n, ld, workspace, workspace_bytes)) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool timing = getenv("VMCPDE_EIGH_TIMING") != nullptr;
+  cudaEvent_t evt[4];
+  if (timing) { for (auto& e_ : evt) cudaEventCreate(&e_); cudaEventRecord(evt[0], s); }
+  if (int rc = eigh_factor_impl(w, S, n, ld, ev, VT, s, timing ? evt : nullptr)) return rc;
+  if (timing) cudaEventRecord(evt[2], s);
+  // out of place: Z^T = b.QT -> VT; the other ping-pong buffer is free for the reflector transpose
+  if (int rc = eigh_back_impl(w, S, w.tau, n, ld, w.b.QT, w.b.QT_new, VT, col0, ncols, s)) return rc;
   if (timing) {
     cudaEventRecord(evt[3], s);
     cudaEventSynchronize(evt[3]);
@@ -834,6 +869,40 @@ static int eigh_impl(double* S, int32_t n, int32_t ld, double* ev, double* VT, i
     for (auto& e_ : evt) cudaEventDestroy(e_);
   }
   return 0;
+}
+
+// The eigensolver in two calls, for a multi-GPU solve in which ONE rank factorises while the others still build Gram
+// matrices: vmcpde_eigh_factor runs scaling, tridiagonalisation and divide & conquer (the serial part) and leaves the three
+// things the back-transformation needs -- the reflectors (in S), tau[n] and Z^T (rows = eigenvectors of the tridiagonal
+// matrix, rows x ld with rows = n rounded up to 128) -- in caller-owned buffers that can be broadcast;
+// vmcpde_eigh_backtransform applies the reflectors to a 128-aligned slice of eigenvectors on any rank.
+// factor + backtransform of all columns == vmcpde_eigh, bit for bit.  Blocked path only (n >= 384, padded ld).
+extern "C" __attribute__((visibility("default"))) int vmcpde_eigh_factor(double* S, int32_t n, int32_t ld, double* ev, double* ZT,
+                                                                        double* tau, void* workspace, size_t workspace_bytes,
+                                                                        vmcpde_stream stream) {
+  VMC_REQUIRE(S && ev && ZT && tau && workspace, "vmcpde_eigh_factor: null pointer");
+  EighWs w;
+  if (int rc = eigh_layout(w, n, ld, workspace, workspace_bytes)) return rc;
+  if (!w.blocked) return set_error(VMCPDE_EUNSUPPORTED, "vmcpde_eigh_factor: needs the blocked path (n >= 384, ld a multiple of 128)");
+  cudaStream_t s = (cudaStream_t)stream;
+  // the divide & conquer only writes the n x n corner: the padding of Z^T must be zero for the back-transformation
+  VMC_CUDA_CHECK(cudaMemsetAsync(ZT, 0, w.rows * ld * 8, s));
+  if (int rc = eigh_factor_impl(w, S, n, ld, ev, ZT, s, nullptr)) return rc;
+  if (w.b.QT != ZT) VMC_CUDA_CHECK(cudaMemcpyAsync(ZT, w.b.QT, w.rows * ld * 8, cudaMemcpyDeviceToDevice, s));
+  VMC_CUDA_CHECK(cudaMemcpyAsync(tau, w.tau, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int vmcpde_eigh_backtransform(const double* reflectors, const double* tau,
+                                                                               const double* ZT, int32_t n, int32_t ld, double* VT,
+                                                                               int32_t col0, int32_t ncols, void* workspace,
+                                                                               size_t workspace_bytes, vmcpde_stream stream) {
+  VMC_REQUIRE(reflectors && tau && ZT && VT && workspace, "vmcpde_eigh_backtransform: null pointer");
+  VMC_REQUIRE(VT != ZT && VT != reflectors, "vmcpde_eigh_backtransform: VT must not alias the inputs");
+  EighWs w;
+  if (int rc = eigh_layout(w, n, ld, workspace, workspace_bytes)) return rc;
+  if (!w.blocked) return set_error(VMCPDE_EUNSUPPORTED, "vmcpde_eigh_backtransform: needs the blocked path (n >= 384, ld a multiple of 128)");
+  return eigh_back_impl(w, const_cast<double*>(reflectors), tau, n, ld, ZT, w.QTb, VT, col0, ncols, (cudaStream_t)stream);
 }
 
 extern "C" __attribute__((visibility("default"))) int vmcpde_eigh(double* S, int32_t n, int32_t ld, double* ev, double* VT,

@@ -57,6 +57,16 @@ def allreduce_(t):
     return t
 
 
+def broadcast_(t, src=0):
+    """In-place broadcast of a tensor from rank `src` (no-op for a single process)."""
+    global communicationTime
+    if _initialized() and dist.get_world_size() > 1:
+        t0 = time.perf_counter()
+        dist.broadcast(t, src=src)
+        communicationTime += time.perf_counter() - t0
+    return t
+
+
 def distribute_sampling(numSamples, localDevices=None, numChainsPerDevice=1):
     """mpi_wrapper.py:68-110, same arithmetic."""
     global globNumSamples

@@ -53,7 +53,8 @@ class LazyGram:
         out = _kernels.zeros(self._Pp)
         if self._t is None:
             self._t = _kernels.empty(max(self._n, 1))
-        _kernels.gram_matvec(self._O, self._n, self._Pp, self._w, vp, self._t, out)
+        if self._n > 0:      # a solver rank of a pipelined solve may own no samples
+            _kernels.gram_matvec(self._O, self._n, self._Pp, self._w, vp, self._t, out)
         mpi.allreduce_(out)
         return out[:self._P] / self._N
 
@@ -89,6 +90,22 @@ class LazyGram:
         return a.astype(dtype) if dtype is not None else a
 
 
+# seconds of the serial eigensolver stages (tridiagonalisation + divide & conquer) on one B200 by matrix size, measured with
+# bench.py / tools/probe_eigh.py (profiles/); log-log interpolation in between
+_SOLVER_SECONDS = ((384, 0.008), (1024, 0.022), (2053, 0.050), (4096, 0.12), (8187, 0.33), (12000, 0.85), (16385, 2.45), (25600, 9.0))
+
+
+def solver_seconds(P):
+    pts = _SOLVER_SECONDS
+    if P <= pts[0][0]:
+        return pts[0][1]
+    for (p0, t0), (p1, t1) in zip(pts, pts[1:]):
+        if P <= p1:
+            a = math.log(P / p0) / math.log(p1 / p0)
+            return math.exp(math.log(t0) + a * (math.log(t1) - math.log(t0)))
+    return pts[-1][1] * (P / pts[-1][0]) ** 3
+
+
 def solve_shard_range(Pp, world, rank):
     """Eigenvector slice [row0, row0 + nrows) of rank `rank` in a sharded solve: the Pp / 128 blocks of 128 eigenvectors
     are dealt contiguously; ranks beyond the block count get an empty slice."""
@@ -110,6 +127,10 @@ class TDVP:
                                        # operator on the resident O (LazyGram; stepper.py:71 only needs v^T SExp v); False: skip
     computeSNR: bool = True            # snr is logged by main.py:187 and gates the solve when useSNR
     shardSolve: bool = True            # several ranks: shard the post-tridiagonal O(P^3) stages over eigenvectors
+    pipelineSolve: bool = True         # several ranks: one rank runs the serial eigensolver stages while the others build
+                                       # the SExp / C_EO Grams (sample shares balanced by sample_partition)
+    solverRank: int = 0
+    solverShare: object = None         # None: cost model; else fraction of an equal sample share given to the solver rank
     chunkSamples: int = 0              # samples per chunk (0 = choose from free memory)
     memoryFraction: float = 0.45       # share of free device memory the O buffer may take
 
@@ -145,7 +166,9 @@ class TDVP:
     def _buffers(self, P, Pp):
         if self._bufP != (P, Pp):
             z = _kernels.zeros
-            self._second = z(3 * Pp * Pp + Pp + 8)            # [S0 | SExp | CEO | Fsum | var_sum] packed for one all-reduce
+            # [S0 | Fsum | var_sum | SExp | CEO]: one all-reduce, or two (head = what the solve needs first) when pipelined
+            self._second = z(3 * Pp * Pp + Pp + 8)
+            self._ZT = self._tau = None
             self._Sshift = None
             self._Swork = _kernels.empty(Pp, Pp)
             self._VT = z(Pp, Pp)
@@ -157,53 +180,57 @@ class TDVP:
 
     def _mats(self, Pp):
         s = self._second
+        head = Pp * Pp + Pp + 8
         S0 = s[0:Pp * Pp].view(Pp, Pp)
-        SExp = s[Pp * Pp:2 * Pp * Pp].view(Pp, Pp)
-        CEO = s[2 * Pp * Pp:3 * Pp * Pp].view(Pp, Pp)
-        Fsum = s[3 * Pp * Pp:3 * Pp * Pp + Pp]
-        var_sum = s[3 * Pp * Pp + Pp:3 * Pp * Pp + Pp + 1]
+        Fsum = s[Pp * Pp:Pp * Pp + Pp]
+        var_sum = s[Pp * Pp + Pp:Pp * Pp + Pp + 1]
+        SExp = s[head:head + Pp * Pp].view(Pp, Pp)
+        CEO = s[head + Pp * Pp:head + 2 * Pp * Pp].view(Pp, Pp)
         return S0, SExp, CEO, Fsum, var_sum
 
     # ---- pieces of get_tdvp_equation (tdvp.py:36-52) on one chunk ------------------------------------
     def _pass1_chunk(self, E, lp, O, n, ldo, first):
         _kernels.moments1(E, lp, O, n, ldo, first)
 
-    def _pass2_chunk(self, E, lp, O, n, n_pad, ldo, Pp, meanO, meanE, scratch):
+    def _pass2_chunk(self, E, lp, O, n, n_pad, ldo, Pp, meanO, meanE, scratch, which="all"):
+        """Centring + force vector (which != "rest"), then the weighted Grams: "all" = S0, SExp, C_EO in one launch;
+        "s0" = only S0 (what the solve needs first); "rest" = SExp and C_EO on the already centred O."""
         S0, SExp, CEO, Fsum, var_sum = self._mats(Pp)
         dE, wE, wLp = scratch
-        if n_pad > n:
-            O[n:n_pad].zero_(); wE[n:n_pad].zero_(); wLp[n:n_pad].zero_()
-        _kernels.center_force(O, n, ldo, meanO, E, lp, meanE, dE, wE, wLp, Fsum, var_sum)
-        mats, weights = [S0], [None]
-        if self.computeSExp is True or (self.computeSExp and not self._lazy_ok):
-            mats.append(SExp); weights.append(wLp)
-        if self.computeSNR and self.solver == "eigh":
-            mats.append(CEO); weights.append(wE)
-        _kernels.gram(O, n_pad, ldo, Pp, weights, mats)
+        if which != "rest":
+            if n_pad > n:
+                O[n:n_pad].zero_(); wE[n:n_pad].zero_(); wLp[n:n_pad].zero_()
+            _kernels.center_force(O, n, ldo, meanO, E, lp, meanE, dE, wE, wLp, Fsum, var_sum)
+        mats, weights = ([S0], [None]) if which != "rest" else ([], [])
+        if which != "s0":
+            if self.computeSExp is True or (self.computeSExp and not self._lazy_ok):
+                mats.append(SExp); weights.append(wLp)
+            if self.computeSNR and self.solver == "eigh":
+                mats.append(CEO); weights.append(wE)
+        if mats:
+            _kernels.gram(O, n_pad, ldo, Pp, weights, mats)
 
-    def _finish(self, P, Pp, N, first):
-        """All-reduce of the second moments, normalisation, regularised solve (tdvp.py:50-51,57-94)."""
+    def _finish(self, P, Pp, N, first, pipeline=None):
+        """All-reduce of the second moments, normalisation, regularised solve (tdvp.py:50-51,57-94).
+
+        `pipeline` (several ranks, blocked eigensolver): a callable that launches the SExp / C_EO Grams of this rank.  Then
+        the S0 block is all-reduced first, the solver rank runs the serial stages of the eigensolver (tridiagonalisation,
+        divide & conquer) while the other ranks build those Grams, and the factors are broadcast for the sharded
+        back-transformation -- the serial stages leave the critical path of every rank but one."""
         S0, SExp, CEO, Fsum, var_sum = self._mats(Pp)
-        mpi.allreduce_(self._second)
+        head = Pp * Pp + Pp + 8
+        if pipeline is None:
+            mpi.allreduce_(self._second)
+        else:
+            mpi.allreduce_(self._second[:head])
         inv = 1.0 / N
         _kernels.sym_finalize(S0, Pp, inv)
         eager_sexp = self.computeSExp is True or (self.computeSExp and not self._lazy_ok)
-        if eager_sexp:
-            _kernels.sym_finalize(SExp, Pp, inv)
         use_ceo = self.computeSNR and self.solver == "eigh"
-        if use_ceo:
-            _kernels.sym_finalize(CEO, Pp, inv)
         F = Fsum * inv
         self.ElocVar = (var_sum[0] * inv).clone()
         # S0 / SExp / S (P x P, 0.5 GB each at P = 8187) are views of the persistent buffers: valid until the next call
         self.S0, self.F0 = S0[:P, :P], F[:P]
-        if eager_sexp:
-            self.SExp = SExp[:P, :P]
-        elif self.computeSExp:
-            O, n, n_pad, w = self._lazy_src
-            self.SExp = LazyGram(self, self._lazy_gen, O, n, n_pad, Pp, P, w, N)
-        else:
-            self.SExp = None
         S = S0
         if self.diagonalShift > 1e-10:  # tdvp.py:50-51
             if self._Sshift is None:
@@ -214,19 +241,49 @@ class TDVP:
         meanE2 = float(first[2]) * inv  # mean(Eloc**2) of the un-centred local term (tdvp.py:93); host scalar
         ev, VtF, rhoVar, snr, invEv, update, w0, w1 = [self._vecs[i] for i in range(8)]
         self._Swork.copy_(S)
-        if self.solver == "eigh":
+        R, rank = mpi.comm.Get_size(), mpi.comm.Get_rank()
+        if pipeline is not None:
             ws = _kernels.workspace(_kernels.eigh_workspace_bytes(P, Pp))
-            R, rank = mpi.comm.Get_size(), mpi.comm.Get_rank()
+            if self._ZT is None:
+                self._ZT, self._tau = _kernels.empty(Pp, Pp), _kernels.zeros(2 * Pp)
+            if rank == self.solverRank:
+                _kernels.eigh_factor(self._Swork, P, Pp, ev, self._ZT, self._tau[:Pp], ws)
+                self._tau[Pp:].copy_(ev)
+            pipeline()
+            mpi.allreduce_(self._second[head:])
+            mpi.broadcast_(self._Swork, self.solverRank)        # the reflectors
+            mpi.broadcast_(self._ZT, self.solverRank)           # eigenvectors of the tridiagonal matrix (rows)
+            mpi.broadcast_(self._tau, self.solverRank)          # tau | ev
+            ev.copy_(self._tau[Pp:])
+        else:
+            ws = None
+        if eager_sexp:
+            _kernels.sym_finalize(SExp, Pp, inv)
+        if use_ceo:
+            _kernels.sym_finalize(CEO, Pp, inv)
+        if eager_sexp:
+            self.SExp = SExp[:P, :P]
+        elif self.computeSExp:
+            O, n, n_pad, w = self._lazy_src
+            self.SExp = LazyGram(self, self._lazy_gen, O, n, n_pad, Pp, P, w, N)
+        else:
+            self.SExp = None
+        if self.solver == "eigh":
+            if ws is None:
+                ws = _kernels.workspace(_kernels.eigh_workspace_bytes(P, Pp))
             nblk = Pp // 128
             self._vt_range = None
             if R > 1 and nblk >= R and self.shardSolve:
-                # Tridiagonalisation and divide & conquer are replicated (every rank holds the all-reduced S); the O(P^3)
-                # stages after them -- back-transformation, V^T C V for the SNR, the update -- are sharded over the
-                # eigenvector index in blocks of 128 and joined by one all-reduce of 5 P doubles.
+                # The O(P^3) stages after the serial ones -- back-transformation, V^T C V for the SNR, the update -- are sharded
+                # over the eigenvector index in blocks of 128 and joined by one all-reduce of 5 P doubles.  The serial stages
+                # themselves are either replicated (every rank holds the all-reduced S) or, pipelined, run on the solver rank.
                 row0, nrows = solve_shard_range(Pp, R, rank)
                 vec = self._vecs[1:6]
                 vec.zero_()
-                _kernels.eigh_cols(self._Swork, P, Pp, ev, self._VT, row0, nrows, ws)
+                if pipeline is not None:
+                    _kernels.eigh_backtransform(self._Swork, self._tau[:Pp], self._ZT, P, Pp, self._VT, row0, nrows, ws)
+                else:
+                    _kernels.eigh_cols(self._Swork, P, Pp, ev, self._VT, row0, nrows, ws)
                 _kernels.solve_tail_range(ev, self._VT, P, Pp, F, CEO if use_ceo else None, float(N), self.svdTol, self.snrTol,
                                           self.useSNR, row0, nrows, VtF, rhoVar if use_ceo else None, snr if use_ceo else None,
                                           invEv, update, ws)
@@ -255,6 +312,43 @@ class TDVP:
             self.ev = self.VtF = self.invEv = self.rhoVar = self.snr = None
         self.solverResidual, self.tdvp_error = self._scal[0].clone(), self._scal[1].clone()
         return update[:P].clone()
+
+    # ---- sample partition of the fused path -----------------------------------------------------------
+    def _pipelined(self, R, P, Pp):
+        """The solver-rank pipeline applies to a multi-rank eigen-solve on the blocked path with a sharded back-transformation."""
+        return (R > 1 and self.pipelineSolve and self.solver == "eigh" and self.shardSolve and Pp // 128 >= R
+                and P >= 384 and P <= 25 * 1024)
+
+    def sample_partition(self, N, R, P):
+        """[(first, n)] per rank.  Equal contiguous shards unless the solve is pipelined: then the solver rank,
+        which spends E(P) seconds in the serial stages of the eigensolver while the others build the SExp / C_EO Grams, gets
+        n0 samples and the others n1 with (2/3) g (n1 - n0) = E, g = seconds of the three Grams per sample -- all ranks
+        finish together.  Deterministic in (N, R, P): a model of the B200, not a measurement of the run, so the summation
+        order of a run is reproducible.  `solverShare` (fraction of an equal share) overrides the model."""
+        base, rem = N // R, N % R
+        equal = [(r * base + min(r, rem), base + (1 if r < rem else 0)) for r in range(R)]
+        Pp = _kernels.round_up(P, 128)
+        if not self._pipelined(R, P, Pp):
+            return equal
+        if self.solverShare is not None:
+            n0 = int(max(0.0, min(1.0, float(self.solverShare))) * N / R)
+        else:
+            g = 3.0 * P * (P + 1.0) / 34.5e12                      # DMMA Gram rate measured on B200 (DESIGN.md section 4)
+            delta = 1.5 * solver_seconds(P) / g
+            n0 = int(max(0.0, (N - (R - 1) * delta) / R))
+        n0 = min(n0 // 16 * 16, N)
+        others = R - 1
+        b2, r2 = (N - n0) // others, (N - n0) % others
+        out, first, k = [], 0, 0
+        for r in range(R):
+            if r == self.solverRank:
+                n = n0
+            else:
+                n = b2 + (1 if k < r2 else 0)
+                k += 1
+            out.append((first, n))
+            first += n
+        return out
 
     # ---- reference entry points on materialised arrays -----------------------------------------------
     def get_tdvp_equation(self, Eloc, gradients, logProbs):
@@ -374,14 +468,15 @@ class TDVP:
     def _fused_rhs(self, psi, evolutionEq, t, N, tic, toc):
         h = psi.net.handle
         P, Pp, d = h.P, h.Pp, h.dim
-        first_idx, n_local = mpi.shard_range(N)
+        R, rank = mpi.comm.Get_size(), mpi.comm.Get_rank()
+        first_idx, n_local = self.sample_partition(N, R, P)[rank]
         key = psi.sampler.next_key()                       # sampler.py:73 (one key per psi.sample call)
         chi2_all = psi.chi2_draws(n_local, first_idx, N)
         eq = evolutionEq.equation_struct(t)
         self._buffers(P, Pp).zero_()
         rows, stored = self._plan_chunks(n_local, Pp)
         self._gen += 1
-        self._lazy_ok = stored and n_local > 0
+        self._lazy_ok = stored
         if self.computeSExp and self.computeSExp is not True and mpi.comm.Get_size() > 1:
             # LazyGram.dot is collective: every rank must take the same branch
             flag = torch.tensor([1.0 if self._lazy_ok else 0.0], dtype=torch.float64, device=global_defs.device())
@@ -424,6 +519,12 @@ class TDVP:
         toc("solve TDVP eqn.", t0)
         # pass 2: centring, force vector, weighted Grams (tdvp.py:40-47); local terms are re-evaluated chunk by chunk
         # when the whole O does not fit in memory (same key and counters -> identical samples)
+        pipelined = self._pipelined(R, P, Pp)
+        if pipelined:   # needs the whole rank-local O resident on every rank
+            flag = torch.tensor([0.0 if stored else 1.0], dtype=torch.float64, device=global_defs.device())
+            mpi.allreduce_(flag)
+            pipelined = bool(flag.item() == 0.0)
+        which = "s0" if pipelined else "all"
         for c0, cn in chunks:
             if cn == 0:
                 continue
@@ -431,11 +532,16 @@ class TDVP:
                 local_chunk(c0, cn, False)
             t0 = tic()
             self._pass2_chunk(E_all[c0:c0 + cn], lp_all[c0:c0 + cn], O, cn, _kernels.round_up(cn, 16), Pp, Pp, meanO, meanE,
-                              self._scratch)
+                              self._scratch, which)
             toc("solve TDVP eqn.", t0)
         t0 = tic()
         self._lazy_src, self._lazy_gen = (O, n_local, _kernels.round_up(max(n_local, 1), 16), self._scratch[2]), self._gen
-        update = self._finish(P, Pp, N, first)
+        rest = None
+        if pipelined:
+            def rest():
+                if n_local > 0:
+                    self._pass2_chunk(E_all, lp_all, O, n_local, _kernels.round_up(n_local, 16), Pp, Pp, meanO, meanE, self._scratch, "rest")
+        update = self._finish(P, Pp, N, first, pipeline=rest)
         toc("solve TDVP eqn.", t0)
         return update, x_all, lp_all, E_all
 
@@ -447,18 +553,21 @@ class TDVP:
         first = _kernels.zeros(d + 2)
         first[d + 1] = -float("inf")
         same = E_all.shape[0] == n
-        _kernels.obs_first(x, lp, E_all if same else None, n, d, first, ws)
+        if n > 0:            # a solver rank of a pipelined solve may own no samples: its sums stay zero
+            _kernels.obs_first(x, lp, E_all if same else None, n, d, first, ws)
         if same:
             mx = first[d + 1].clone()
         else:  # observables were re-sampled: max E_loc still refers to the TDVP samples (tdvp.py:150)
             tmp = _kernels.zeros(3)
             tmp[2] = -float("inf")
-            _kernels.obs_first(E_all.reshape(-1, 1), None, E_all, E_all.shape[0], 1, tmp, ws)
+            if E_all.shape[0] > 0:
+                _kernels.obs_first(E_all.reshape(-1, 1), None, E_all, E_all.shape[0], 1, tmp, ws)
             mx = tmp[2].clone()
         mpi.allreduce_(first[:d + 1])
         mean = (first[:d] / n_glob).contiguous()
         central = _kernels.zeros(d * d + 4 * d)
-        _kernels.obs_central(x, n, d, mean, central, ws)
+        if n > 0:
+            _kernels.obs_central(x, n, d, mean, central, ws)
         mpi.allreduce_(central)
         central = central / n_glob
         info = {}
