@@ -163,9 +163,10 @@ int vmcpde_gemm_tn_splitk(const double* X, int64_t ldx, const double* Y, int64_t
  * of 128, K of 16); the lower tiles of Out are not touched. */
 int vmcpde_syrk_tn(const double* X, int64_t ldx, double* Out, int64_t ldo, int32_t M, int64_t K, double alpha,
                    double beta, vmcpde_stream stream);
-/* Register-resident DMMA issue rate of the device in TFLOP/s (roofline denominator of the S build).
- * Synchronises the device. */
-int vmcpde_dmma_peak(double* tflops_out);
+/* One launch of a register-resident DMMA.8x8x4 loop (148 x 4 CTAs x 8 warps): the FP64 tensor-pipe probe that gives the
+ * roofline denominator of the S build (MEASURED_PEAKS.json has no FP64 entry).  `scratch`: 8 bytes of device memory.
+ * *flops = floating-point operations of the launch; the caller times it with events on `stream`.  No allocation, no sync. */
+int vmcpde_dmma_probe(void* scratch, int32_t iters, double* flops, vmcpde_stream stream);
 
 /* ---- (4) regularised solve -------------------------------------------------------------------- */
 /* Symmetric eigendecomposition on the device, replacing np.linalg.eigh at tdvp.py:61-64.

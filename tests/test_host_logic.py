@@ -199,12 +199,21 @@ def test_two_rank_reductions_over_gloo():
 
 def test_bench_reference_arm_runs_on_the_cpu():
     """bench.py --impl reference (the oracle port timed on the host cores): a reduced sample goes through every section
-    (sampling, local terms, Grams, eigh block, EO@V) and extrapolates to a positive step time."""
+    (sampling, local terms, Grams, eigh, EO@V) and extrapolates to a positive step time; all host threads are claimed even
+    under torchrun's OMP_NUM_THREADS=1."""
     import importlib.util, pathlib
     spec = importlib.util.spec_from_file_location("bench", pathlib.Path(__file__).resolve().parents[1] / "bench.py")
     bench = importlib.util.module_from_spec(spec); spec.loader.exec_module(bench)
-    sec, parts = bench.cpu_step_estimate(n_s=64, p_s=256)
+    cores = bench.use_all_host_threads()
+    assert cores == len(os.sched_getaffinity(0)) == torch.get_num_threads()
+    sec, parts, note = bench.cpu_step_estimate("C3", n_s=64, p_block=256)
     assert sec > 0 and set(parts) == {"sampling_s", "local_terms_s", "two_grams_and_F_s", "eigh_s", "EO_at_V_s"}
-    assert all(v >= 0 for v in parts.values())
+    assert all(v >= 0 for v in parts.values()) and "256 block" in note
+    lin = bench.cpu_linearity("C2", sizes=(64, 128))
+    assert set(lin) == {"64", "128"} and lin["64"]["total_per_sample_s"] > 0
     cfg = bench.workload_config(4)
     assert cfg["num_params"] == 8187 and cfg["n_samples"] == 2 ** 18 and "workload" in cfg
+    assert bench.workload_config(2, "C4")["num_params"] == 16385 and bench.metric_name("C3") == bench.METRIC
+    rep = bench.parity_report("C3", {"ev_max": 1.0, "ev_sum": 2.0, "update_S0_update": 3.0, "F_norm": 1.0, "tdvp_error": 0.5,
+                                     "entropy": 1.0, "solver_residual": 1e-10})
+    assert "values" in rep

@@ -335,7 +335,21 @@ def sum_exp(logp_, n, out, ws):
     _lib.check(_lib.load().vmcpde_sum_exp(_lib.ptr(logp_), int(n), _lib.ptr(out), _lib.ptr(ws), _lib.stream()))
 
 
-def dmma_peak_tflops():
-    v = C.c_double(0.0)
-    _lib.check(_lib.load().vmcpde_dmma_peak(C.byref(v)))
-    return v.value
+def dmma_peak_tflops(reps=9, warm=150, iters=8000):
+    """FP64 tensor-pipe rate of this GPU: `warm` untimed launches of the DMMA probe to bring the clocks up (a cold GPU
+    under-reports by ~20 %), then the MEDIAN of `reps` timed ones.  Returns (TFLOP/s, list of all timed values)."""
+    scratch = zeros(1)
+    fl = C.c_double(0.0)
+    L = _lib.load()
+    for _ in range(warm):
+        _lib.check(L.vmcpde_dmma_probe(_lib.ptr(scratch), iters, C.byref(fl), _lib.stream()))
+    vals = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(L.vmcpde_dmma_probe(_lib.ptr(scratch), iters, C.byref(fl), _lib.stream()))
+        e1.record()
+        e1.synchronize()
+        vals.append(fl.value / (e0.elapsed_time(e1) * 1e-3) * 1e-12)
+    vals.sort()
+    return vals[len(vals) // 2], vals

@@ -37,7 +37,7 @@ SIGNATURES = {
     "vmcpde_gram": (C.c_int, [_vp, _i64, _i64, _i32, _i32, C.POINTER(_vp), C.POINTER(_vp), _vp]),
     "vmcpde_sym_finalize": (C.c_int, [_vp, _i32, _dbl, _vp]),
     "vmcpde_diag_shift": (C.c_int, [_vp, _vp, _i32, _i32, _dbl, _vp]),
-    "vmcpde_dmma_peak": (C.c_int, [C.POINTER(_dbl)]),
+    "vmcpde_dmma_probe": (C.c_int, [_vp, _i32, C.POINTER(_dbl), _vp]),
     "vmcpde_gemm_tn_splitk": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i64, _i32, _vp]),
     "vmcpde_syrk_tn": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i64, _dbl, _dbl, _vp]),
     "vmcpde_gemm_tn": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i64, _dbl, _dbl, _vp]),

@@ -537,35 +537,15 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_gemm_tn_splitk(cons
   return 0;
 }
 
-// Measures the register-resident DMMA rate of the device (FP64 tensor peak used as the roofline
-// denominator of the S build).  Synchronises the device.
-extern "C" __attribute__((visibility("default"))) int vmcpde_dmma_peak(double* tflops_out) {
+// One launch of the register-resident DMMA loop (FP64 tensor peak probe: the roofline denominator of the S build).
+// `scratch` is 8 bytes of device memory; the caller times the launch with events on `stream` and divides *flops by it.
+// No allocation, no synchronisation.
+extern "C" __attribute__((visibility("default"))) int vmcpde_dmma_probe(void* scratch, int32_t iters, double* flops, vmcpde_stream stream) {
   using namespace vmc;
-  double* d = nullptr;
-  VMC_CUDA_CHECK(cudaMalloc(&d, 8));
-  cudaEvent_t e0, e1;
-  cudaEventCreate(&e0);
-  cudaEventCreate(&e1);
-  const int iters = 8000, blocks = num_sms() * 4;
-  // bring the clocks up first (a cold GPU under-reports by ~20%): ~0.5 s of the same loop, untimed
-  for (int w = 0; w < 60; ++w) dmma_peak_kernel<<<blocks, 256>>>(d, iters);
-  cudaDeviceSynchronize();
-  double best = 0.0;
-  for (int rep = 0; rep < 10; ++rep) {
-    cudaEventRecord(e0);
-    dmma_peak_kernel<<<blocks, 256>>>(d, iters);
-    cudaEventRecord(e1);
-    cudaEventSynchronize(e1);
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, e0, e1);
-    const double flops = (double)blocks * 8 /*warps*/ * iters * 16.0 * 512.0;
-    const double tf = flops / (ms * 1e-3) * 1e-12;
-    if (tf > best) best = tf;
-  }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  cudaFree(d);
+  VMC_REQUIRE(scratch && iters > 0, "vmcpde_dmma_probe: bad arguments");
+  const int blocks = num_sms() * 4;
+  dmma_peak_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((double*)scratch, iters);
   VMC_LAUNCH_CHECK("dmma_peak_kernel");
-  *tflops_out = best;
+  if (flops) *flops = (double)blocks * 8 /*warps*/ * iters * 16.0 * 512.0;
   return 0;
 }
