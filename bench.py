@@ -304,6 +304,38 @@ def run_ours(args):
         ms_chol = tc0.elapsed_time(tc1) / 2
         del Tc
         variants = {"lazy_SExp_ms": ms_lazy, "cholesky_ms": ms_chol}
+        # third variant: the north star's "FP32-split path with stated tolerance": SExp and the SNR covariance on tcgen05
+        # (bf16 x 3 split operands, TMEM accumulators); S0 stays FP64, theta_dot is bit-identical (tests).  Same step, same work.
+        Ts = _tdvp.TDVP(gramPrecision="split")
+        vs.set_parameters(theta_init)
+        sts = _stepper.FixedStepper(timeStep=cfg["dt"], mode='Heun', maxStep=1e-2, increase_fac=1.3)
+        sts.step(0, Ts, vs.get_parameters(), **rhs)
+        barrier()
+        split_ev = []
+        orig_split = _kernels.gram_split
+
+        def timed_split(*a_):
+            e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0_.record(); orig_split(*a_); e1_.record()
+            split_ev.append((e0_, e1_, a_[1]))
+        _kernels.gram_split = timed_split
+        ts0 = torch.cuda.Event(enable_timing=True); ts1 = torch.cuda.Event(enable_timing=True)
+        ts0.record()
+        for _ in range(2):
+            y, _, _ = sts.step(0, Ts, vs.get_parameters(), **rhs)
+            vs.set_parameters(y)
+        ts1.record()
+        barrier()
+        _kernels.gram_split = orig_split
+        variants["split_ms"] = ts0.elapsed_time(ts1) / 2
+        sp_ms = sum(a_.elapsed_time(b_) for a_, b_, _ in split_ev)
+        Pp_ = _kernels.round_up(P, 128)
+        tl_ = Pp_ // 128
+        sp_flops = sum(tl_ * (tl_ + 1) / 2 * 128 * 128 * ((n_ + 255) // 256 * 256) * 2.0 * 6 for _, _, n_ in split_ev)
+        variants["split_kernel"] = {"launches": len(split_ev), "ms_per_launch": sp_ms / max(len(split_ev), 1),
+                                    "bf16_tflops": sp_flops / (sp_ms * 1e-3) * 1e-12 if sp_ms else None,
+                                    "fp64_equivalent_tflops": sum(n_ * P * (P + 1.0) for _, _, n_ in split_ev) / (sp_ms * 1e-3) * 1e-12 if sp_ms else None}
+        del Ts
         if args.adaptive:   # C3 with the adaptive integrator -- one attempt = 5 right-hand sides + the SExp error norm
             out_a = {}
             for mode in (True, "lazy"):
@@ -321,13 +353,13 @@ def run_ours(args):
             variants["adaptive_heun"] = out_a
     # ---- max over ranks of the timings; per-rank stage times gathered
     mine = torch.tensor([ms, ms_e2e, variants.get("lazy_SExp_ms", 0.0), variants.get("cholesky_ms", 0.0), gram_ms, gram_flops, serial_ms,
-                         back_ms], device="cuda", dtype=torch.float64)
+                         back_ms, variants.get("split_ms", 0.0)], device="cuda", dtype=torch.float64)
     allv = [mine]
     if world > 1:
         allv = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(allv, mine)
     allv = torch.stack(allv).cpu().numpy()
-    ms, ms_e2e, ms_lazy, ms_chol = allv[:, 0].max(), allv[:, 1].max(), allv[:, 2].max(), allv[:, 3].max()
+    ms, ms_e2e, ms_lazy, ms_chol, ms_split = allv[:, 0].max(), allv[:, 1].max(), allv[:, 2].max(), allv[:, 3].max(), allv[:, 8].max()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -380,7 +412,22 @@ def run_ours(args):
         "last_entropy": ent,
     }
     if variants:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        bf16_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        sk = variants.get("split_kernel", {})
         line["variants"] = {"lazy_SExp_steps_per_s": 1e3 / ms_lazy, "cholesky_shift1e-4_steps_per_s": 1e3 / ms_chol,
+                            "split_precision_steps_per_s": 1e3 / ms_split,
+                            "split_precision": {"what": "TDVP(gramPrecision='split'): SExp and the SNR covariance on tcgen05 (bf16 x 3 split operands, "
+                                                        "6 products per logical product, FP32 TMEM accumulation over 256 samples, FP64 sums; stated "
+                                                        "tolerance 1e-6); S0 on FP64 DMMA; theta_dot bit-identical to the FP64 run",
+                                                "kernel": "gram_split_kernel (rank 0)", **sk,
+                                                "roofline": {"bound": "tensor", "achieved": sk.get("bf16_tflops"), "peak": bf16_peak, "unit": "TFLOP/s",
+                                                             "frac": (sk.get("bf16_tflops") / bf16_peak) if sk.get("bf16_tflops") else None,
+                                                             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (else fallback 1400)"}},
                             "note": "TDVP(computeSExp='lazy'): SExp kept as a matrix-free operator on the resident O (2 Grams per RHS "
                                     "instead of 3); cholesky: TDVP(diagonalShift=1e-4, solver='cholesky') replaces the eigen-solve by the "
                                     "tensor-core blocked Cholesky (S0 and SExp Grams only).  Neither is the headline -- the reference forms "

@@ -387,3 +387,31 @@ def test_costfun_mode_and_covariance_mirror_match_the_oracle():
     C = mpi.global_covariance(data)
     ref = data[0].cpu().numpy().T @ data[0].cpu().numpy() / 333
     assert C.shape == (37, 37) and relerr(C, ref) < 1e-13 and float((C - C.T).abs().max()) == 0.0
+
+
+def test_split_precision_grams_leave_the_update_untouched():
+    """TDVP(gramPrecision="split"): SExp and the SNR covariance on the tcgen05 split path.  S0, F and -- with useSNR off --
+    theta_dot, ev, the residual are bit-identical to the FP64 run; SExp agrees to 1e-6 (Frobenius and in the quadratic form
+    the adaptive stepper reads, stepper.py:71), rhoVar to 1e-6 of its largest entry, snr to 1e-3 on the resolved modes."""
+    from vmc_pde_b200 import tdvp
+    smp, vs, eq, spec = build(6, 4, 3, "different_add", "Gauss", "advection_hamiltonian_wDiss", np.array([1., 0, 0, 1, 0, 0]))
+    theta = vs.get_parameters().clone()
+    key0 = vs.sampler.key.copy()
+    out = {}
+    for mode in ("fp64", "split"):
+        vs.sampler.key = key0.copy(); vs.set_parameters(theta)
+        T = tdvp.TDVP(gramPrecision=mode)
+        upd, info = T(theta, 0.0, psi=vs, evolutionEq=eq, nSamplesTDVP=6000, nSamplesObs=6000, timings=None)
+        out[mode] = (upd.clone(), T.S0.clone(), T.SExp.clone(), T.ev.clone(), T.snr.clone(), T.rhoVar.clone(), float(T.solverResidual))
+    a, b = out["fp64"], out["split"]
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[3], b[3]) and a[6] == b[6]
+    assert float((a[2] - b[2]).norm() / a[2].norm()) < 1e-6
+    v = torch.linspace(-1, 1, vs.numParameters, device="cuda", dtype=torch.float64)
+    assert abs(float(v @ b[2] @ v) / float(v @ a[2] @ v) - 1) < 1e-6
+    # rhoVar_k = v_k^T C v_k - (v_k^T F)^2 inherits an ABSOLUTE error 1e-6 |C| (measured: 2e-10 of the largest entry); the logged
+    # snr of the resolved modes moves by < 1e-3 relative (measured 2e-4 on the weakest of them)
+    assert float((b[5] - a[5]).abs().max()) < 1e-6 * float(a[5].abs().max())
+    big = (a[3] / a[3][-1]).abs() > 1e-6
+    assert float((b[4][big] / a[4][big] - 1).abs().max()) < 1e-3
+    with pytest.raises(ValueError):
+        tdvp.TDVP(gramPrecision="fp16")

@@ -192,6 +192,25 @@ def gram(O, n, ldo, Pp, weights, mats):
                                        _lib.ptr_array(mats), _lib.stream()))
 
 
+_split_ws = {}
+
+
+def gram_split(O, n, ldo, Pp, weight, S):
+    """S += O^T diag(weight) O on the tcgen05 split-precision path (one matrix; tolerance 1e-6, see include/vmcpde.h)."""
+    _count(2)
+    L = _lib.load()
+    nb = C.c_size_t(0)
+    _lib.check(L.vmcpde_gram_split_workspace_bytes(int(n), int(Pp), C.byref(nb)))
+    dev = _dev()
+    ws = _split_ws.get(dev)
+    if ws is None or ws.numel() < nb.value:
+        _split_ws[dev] = None
+        ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+        _split_ws[dev] = ws
+    _lib.check(L.vmcpde_gram_split(_lib.ptr(O), int(n), int(ldo), int(Pp), _lib.ptr(weight), _lib.ptr(S), _lib.ptr(ws), ws.numel(),
+                                   _lib.stream()))
+
+
 def sym_finalize(S, Pp, scale):
     _count(1)
     _lib.check(_lib.load().vmcpde_sym_finalize(_lib.ptr(S), int(Pp), float(scale), _lib.stream()))

@@ -35,6 +35,8 @@ SIGNATURES = {
     "vmcpde_center_force": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _dbl, _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "vmcpde_gram_matvec": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "vmcpde_gram": (C.c_int, [_vp, _i64, _i64, _i32, _i32, C.POINTER(_vp), C.POINTER(_vp), _vp]),
+    "vmcpde_gram_split_workspace_bytes": (C.c_int, [_i64, _i32, C.POINTER(C.c_size_t)]),
+    "vmcpde_gram_split": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, C.c_size_t, _vp]),
     "vmcpde_sym_finalize": (C.c_int, [_vp, _i32, _dbl, _vp]),
     "vmcpde_diag_shift": (C.c_int, [_vp, _vp, _i32, _i32, _dbl, _vp]),
     "vmcpde_dmma_probe": (C.c_int, [_vp, _i32, C.POINTER(_dbl), _vp]),

@@ -129,6 +129,9 @@ class TDVP:
     shardSolve: bool = True            # several ranks: shard the post-tridiagonal O(P^3) stages over eigenvectors
     pipelineSolve: bool = True         # several ranks: one rank runs the serial eigensolver stages while the others build
                                        # the SExp / C_EO Grams (sample shares balanced by sample_partition)
+    gramPrecision: str = "fp64"        # "fp64": all three Grams on the FP64 DMMA pipe (the reference's arithmetic);
+                                       # "split": SExp and C_EO on tcgen05 with bf16 x 3 split operands (stated tolerance 1e-6;
+                                       # S0, F and hence theta_dot are unchanged when useSNR is off)
     solverRank: int = 0
     solverShare: object = None         # None: cost model; else fraction of an equal sample share given to the solver rank
     chunkSamples: int = 0              # samples per chunk (0 = choose from free memory)
@@ -137,6 +140,8 @@ class TDVP:
     def __post_init__(self):
         if self.solver not in ("eigh", "cholesky"):
             raise ValueError("solver must be 'eigh' or 'cholesky'")
+        if self.gramPrecision not in ("fp64", "split"):
+            raise ValueError("gramPrecision must be 'fp64' or 'split'")
         self._bufP = None
         self._P = None
         self._vt_range = None
@@ -202,13 +207,17 @@ class TDVP:
                 O[n:n_pad].zero_(); wE[n:n_pad].zero_(); wLp[n:n_pad].zero_()
             _kernels.center_force(O, n, ldo, meanO, E, lp, meanE, dE, wE, wLp, Fsum, var_sum)
         mats, weights = ([S0], [None]) if which != "rest" else ([], [])
+        split = []
         if which != "s0":
+            tgt = split if self.gramPrecision == "split" else None
             if self.computeSExp is True or (self.computeSExp and not self._lazy_ok):
-                mats.append(SExp); weights.append(wLp)
+                (tgt.append((wLp, SExp)) if tgt is not None else (mats.append(SExp), weights.append(wLp)))
             if self.computeSNR and self.solver == "eigh":
-                mats.append(CEO); weights.append(wE)
+                (tgt.append((wE, CEO)) if tgt is not None else (mats.append(CEO), weights.append(wE)))
         if mats:
             _kernels.gram(O, n_pad, ldo, Pp, weights, mats)
+        for wgt, mat in split:
+            _kernels.gram_split(O, n, ldo, Pp, wgt, mat)
 
     def _finish(self, P, Pp, N, first, pipeline=None):
         """All-reduce of the second moments, normalisation, regularised solve (tdvp.py:50-51,57-94).
