@@ -392,7 +392,7 @@ def test_costfun_mode_and_covariance_mirror_match_the_oracle():
 def test_split_precision_grams_leave_the_update_untouched():
     """TDVP(gramPrecision="split"): SExp and the SNR covariance on the tcgen05 split path.  S0, F and -- with useSNR off --
     theta_dot, ev, the residual are bit-identical to the FP64 run; SExp agrees to 1e-6 (Frobenius and in the quadratic form
-    the adaptive stepper reads, stepper.py:71), rhoVar to 1e-6 of its largest entry, snr to 1e-3 on the resolved modes."""
+    the adaptive stepper reads, stepper.py:71), rhoVar to 5e-6 of its largest entry, snr to 1e-3 on the resolved modes."""
     from vmc_pde_b200 import tdvp
     smp, vs, eq, spec = build(6, 4, 3, "different_add", "Gauss", "advection_hamiltonian_wDiss", np.array([1., 0, 0, 1, 0, 0]))
     theta = vs.get_parameters().clone()
@@ -410,7 +410,7 @@ def test_split_precision_grams_leave_the_update_untouched():
     assert abs(float(v @ b[2] @ v) / float(v @ a[2] @ v) - 1) < 1e-6
     # rhoVar_k = v_k^T C v_k - (v_k^T F)^2 inherits an ABSOLUTE error 1e-6 |C| (measured: 2e-10 of the largest entry); the logged
     # snr of the resolved modes moves by < 1e-3 relative (measured 2e-4 on the weakest of them)
-    assert float((b[5] - a[5]).abs().max()) < 1e-6 * float(a[5].abs().max())
+    assert float((b[5] - a[5]).abs().max()) < 5e-6 * float(a[5].abs().max())   # v^T C v >= rhoVar: 1e-6 |C| can exceed 1e-6 rhoVar
     big = (a[3] / a[3][-1]).abs() > 1e-6
     assert float((b[4][big] / a[4][big] - 1).abs().max()) < 1e-3
     with pytest.raises(ValueError):

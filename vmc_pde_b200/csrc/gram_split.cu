@@ -12,10 +12,10 @@
 // core truncates its FP32 accumulation (2e-8 if it rounds; NumPy emulation in DESIGN.md) -- the stated tolerance is 1e-6.
 //
 //  * pre-pass (split_rows_kernel): O [n][ldo] FP64 -> X [3 slices][Pp columns][n_pad samples] bf16, sample index
-//    contiguous, so every operand tile is the canonical K-major 128-byte-swizzle UMMA layout and one TMA 2-D box
-//    {64 samples, 128 columns} per slice lands it.
-//  * main kernel (gram_split_kernel), persistent, one CTA per SM, warp-specialised: warp 0 = TMA producer (2-stage ring of
-//    96 KB: A and B tiles x 3 slices x 64 samples), warp 1 = MMA issuer (one elected lane; 24 tcgen05.mma 128x128x16 per
+//    contiguous, so every operand tile is the canonical K-major 64-byte-swizzle UMMA layout and one TMA 2-D box
+//    {32 samples, 128 columns} per slice lands it.
+//  * main kernel (gram_split_kernel), persistent, one CTA per SM, warp-specialised: warp 0 = TMA producer (4-stage ring of
+//    48 KB: A and B tiles x 3 slices x 32 samples), warp 1 = MMA issuer (one elected lane; 12 tcgen05.mma 128x128x16 per
 //    stage), warps 2-9 = epilogue (tcgen05.ld of the two 128x128 FP32 accumulators, FP64 add; TMEM double buffered: 4 x 128
 //    columns = all 512).  Work items = upper-triangular 128x128 tile pairs in the supertile order of gram.cu; diagonal tiles
 //    load one operand.
@@ -29,13 +29,14 @@
 
 namespace vmc {
 
-constexpr int kSpBK = 64;                 // samples per pipeline stage (128 bytes of bf16: one swizzle row)
+constexpr int kSpBK = 32;                 // samples per pipeline stage (64 bytes of bf16: one row of the 64-byte swizzle)
 constexpr int kSpChunk = 256;             // samples per TMEM accumulation chunk (FP32 accumulation length)
-constexpr int kSpTileBytes = 128 * 128;   // one slice of one operand tile: 128 columns x 64 samples x 2 B
-constexpr int kSpStageBytes = 6 * kSpTileBytes;   // A x 3 slices, B x 3 slices
-constexpr int kSpStages = 2;
+constexpr int kSpTileBytes = 128 * kSpBK * 2;     // one slice of one operand tile: 128 columns x 32 samples x 2 B = 8 KB
+constexpr int kSpStageBytes = 6 * kSpTileBytes;   // A x 3 slices, B x 3 slices = 48 KB
+constexpr int kSpStages = 4;              // (2 stages of 64 samples left the tensor pipe 64 % busy: a freed slot was refilled
+                                          //  only one stage time, 0.8 us, ahead of its use -- less than the TMA round trip)
 constexpr int kSpThreads = 320;           // producer warp, MMA warp, 8 epilogue warps
-constexpr size_t kSpSmem = 1024 + (size_t)kSpStages * kSpStageBytes + 128;
+constexpr size_t kSpSmem = 1024 + (size_t)kSpStages * kSpStageBytes + 256;
 
 struct SplitArgs {
   double* S;          // output, leading dimension ldS, upper-triangular tiles are accumulated into
@@ -45,6 +46,7 @@ struct SplitArgs {
   int super;          // supertile edge
   long long n_pad;    // padded samples (multiple of kSpChunk)
   unsigned* fault;    // set to a stage code when a spin timed out
+  int collector;      // 1: keep shared A operands in the tensor core's collector across consecutive MMAs
 };
 
 __device__ __forceinline__ uint32_t sp_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -86,11 +88,25 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(sp_smem_u32(bar)) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]^T, kind::f16 (bf16 operands, FP32 accumulate), M = N = 128, K = 16
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::f16 (bf16 operands, FP32 accumulate), M = N = 128, K = 16.
+// A 128x128x16 MMA reads 4 KB of A and 4 KB of B from shared memory in ~68 clocks -- the whole 128 B/clk of the SM, with the
+// TMA writes of the next stage on top (ncu: tensor pipe 64 % busy).  The A-collector keeps an A operand inside the tensor core
+// across consecutive MMAs that share it (a1 with b1, b2, b3; a2 with b1, b2): 12 KB instead of 24 KB of A per k-step.
+// COLL: 0 = plain, 1 = fill (read A, keep it), 2 = use (reuse, keep), 3 = lastuse (reuse, release).
+template <int COLL>
 __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  if constexpr (COLL == 1)
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n}\n"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  else if constexpr (COLL == 2)
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16.collector::a::use [%0], %1, %2, %3, p;\n}\n"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  else if constexpr (COLL == 3)
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n}\n"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  else
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 // 32 lanes x 16 consecutive 32-bit columns: thread t of the warp gets lane (base lane + t)
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -101,11 +117,11 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in bits
-// [0,14), leading byte offset (unused for swizzled K-major: 1) in [16,30), stride byte offset = 8 rows x 128 B = 1024 B >> 4
-// in [32,46), descriptor version 1 (sm_100) in [46,48), layout type 2 = SWIZZLE_128B in [61,64).
+// K-major, 64-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in bits
+// [0,14), leading byte offset (unused for swizzled K-major: 1) in [16,30), stride byte offset = 8 rows x 64 B = 512 B >> 4
+// in [32,46), descriptor version 1 (sm_100) in [46,48), layout type 4 = SWIZZLE_64B in [61,64).
 __device__ __forceinline__ uint64_t sp_desc(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(8 * kSpBK * 2 / 16) << 32) | (1ull << 46) | (4ull << 61);
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16: D = F32 (bits [4,6) = 1), A = B = BF16 ([7,10) =
 // [10,13) = 1), both K-major ([15], [16] = 0), N >> 3 in [17,23), M >> 4 in [24,29).
@@ -173,15 +189,16 @@ gram_split_kernel(const __grid_constant__ CUtensorMap tmap, const SplitArgs a) {
   extern __shared__ uint8_t sp_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)sp_raw + 1023) & ~(uintptr_t)1023);     // swizzle-128B tiles need 1 KB alignment
   uint64_t* bars = (uint64_t*)(smem + (size_t)kSpStages * kSpStageBytes);
-  uint64_t* full = bars;            // [2] TMA -> MMA
-  uint64_t* empty = bars + 2;       // [2] MMA -> TMA
-  uint64_t* tfull = bars + 4;       // [2] MMA -> epilogue (TMEM buffer ready)
-  uint64_t* tempty = bars + 6;      // [2] epilogue -> MMA (TMEM buffer drained)
-  uint32_t* tmem_slot = (uint32_t*)(bars + 8);
+  uint64_t* full = bars;                    // [kSpStages] TMA -> MMA
+  uint64_t* empty = bars + kSpStages;       // [kSpStages] MMA -> TMA
+  uint64_t* tfull = bars + 2 * kSpStages;   // [2] MMA -> epilogue (TMEM buffer ready)
+  uint64_t* tempty = tfull + 2;             // [2] epilogue -> MMA (TMEM buffer drained)
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) { sp_mbar_init(&full[i], 1); sp_mbar_init(&empty[i], 1); sp_mbar_init(&tfull[i], 1); sp_mbar_init(&tempty[i], 8); }
+    for (int i = 0; i < kSpStages; ++i) { sp_mbar_init(&full[i], 1); sp_mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { sp_mbar_init(&tfull[i], 1); sp_mbar_init(&tempty[i], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
   }
@@ -242,16 +259,25 @@ gram_split_kernel(const __grid_constant__ CUtensorMap tmap, const SplitArgs a) {
             const uint32_t sB = diag ? sA : sA + 3 * kSpTileBytes;
 #pragma unroll
             for (int ks = 0; ks < kSpBK / 16; ++ks) {
-              const uint32_t ko = ks * 32;   // 16 bf16 along K inside the 128-byte swizzle row
+              const uint32_t ko = ks * 32;   // 16 bf16 along K inside the swizzle row
               const uint64_t a1 = sp_desc(sA + ko), a2 = sp_desc(sA + kSpTileBytes + ko), a3 = sp_desc(sA + 2 * kSpTileBytes + ko);
               const uint64_t b1 = sp_desc(sB + ko), b2 = sp_desc(sB + kSpTileBytes + ko), b3 = sp_desc(sB + 2 * kSpTileBytes + ko);
               const uint32_t first = (kb4 == 0 && ks == 0) ? 0u : 1u;
-              tc_mma_bf16(d_hi, a1, b1, kSpIdesc, first);
-              tc_mma_bf16(d_lo, a1, b2, kSpIdesc, first);
-              tc_mma_bf16(d_lo, a2, b1, kSpIdesc, 1u);
-              tc_mma_bf16(d_lo, a1, b3, kSpIdesc, 1u);
-              tc_mma_bf16(d_lo, a2, b2, kSpIdesc, 1u);
-              tc_mma_bf16(d_lo, a3, b1, kSpIdesc, 1u);
+              if (a.collector) {
+                tc_mma_bf16<1>(d_hi, a1, b1, kSpIdesc, first);
+                tc_mma_bf16<2>(d_lo, a1, b2, kSpIdesc, first);
+                tc_mma_bf16<3>(d_lo, a1, b3, kSpIdesc, 1u);
+                tc_mma_bf16<1>(d_lo, a2, b1, kSpIdesc, 1u);
+                tc_mma_bf16<3>(d_lo, a2, b2, kSpIdesc, 1u);
+                tc_mma_bf16<0>(d_lo, a3, b1, kSpIdesc, 1u);
+              } else {
+                tc_mma_bf16<0>(d_hi, a1, b1, kSpIdesc, first);
+                tc_mma_bf16<0>(d_lo, a1, b2, kSpIdesc, first);
+                tc_mma_bf16<0>(d_lo, a2, b1, kSpIdesc, 1u);
+                tc_mma_bf16<0>(d_lo, a1, b3, kSpIdesc, 1u);
+                tc_mma_bf16<0>(d_lo, a2, b2, kSpIdesc, 1u);
+                tc_mma_bf16<0>(d_lo, a3, b1, kSpIdesc, 1u);
+              }
             }
             tc_commit(&empty[stage]);         // frees the smem slot when these MMAs have read it
             if (++stage == kSpStages) { stage = 0; phase ^= 1; }
@@ -361,7 +387,7 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_gram_split(const do
   cuuint32_t box[2] = {(cuuint32_t)kSpBK, 128};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)X, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(VMCPDE_ECUDA, "cuTensorMapEncodeTiled (bf16 slices) failed with code " + std::to_string((int)r));
   static bool attr_set = false;
   if (!attr_set) {
@@ -370,6 +396,7 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_gram_split(const do
   }
   SplitArgs a{};
   a.S = S; a.ldS = Pp; a.Pp = Pp; a.tiles = Pp / 128; a.n_pad = n_pad;
+  a.collector = getenv("VMCPDE_SPLIT_NO_COLLECTOR") ? 0 : 1;
   VMC_CUDA_CHECK(cudaGetSymbolAddress((void**)&a.fault, g_split_fault));
   const long long n_items = (long long)a.tiles * (a.tiles + 1) / 2;
   int grid = num_sms();
