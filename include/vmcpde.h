@@ -172,6 +172,23 @@ int vmcpde_syrk_tn(const double* X, int64_t ldx, double* Out, int64_t ldo, int32
 int vmcpde_gram_split_workspace_bytes(int64_t n, int32_t Pp, size_t* bytes);
 int vmcpde_gram_split(const double* O, int64_t n, int64_t ldo, int32_t Pp, const double* w, double* S, void* workspace,
                       size_t workspace_bytes, vmcpde_stream stream);
+/* ---- cross-GPU sums (mpi_wrapper.py:129-274 as issued from tdvp.py:37-47) for hosts without torch.distributed ----
+ * NCCL is resolved at run time (dlopen libnccl.so.2; the copy already loaded in the process is reused): no link-time
+ * dependency.  `nccl_comm` is an ncclComm_t of that library.  Only the upper-triangular 128x128 tiles of a Gram matrix are
+ * computed, so only they cross NVLink: vmcpde_packed_tiles_len(Pp) doubles per matrix (272 MB instead of 537 MB at Pp = 8192).
+ * vmcpde_allreduce_sum: in-place SUM of `count` doubles (the first moments, P + 4).  vmcpde_allreduce_moments: n_mats (<= 8)
+ * Gram matrices + `n_tail` doubles (force vector, variance sums) packed into `packed` (caller-owned, n_mats * packed_len +
+ * n_tail doubles), ONE ncclAllReduce, unpacked in place.  mats is a HOST array of device pointers. */
+int64_t vmcpde_packed_tiles_len(int32_t Pp);
+int vmcpde_pack_upper_tiles(const double* S, int32_t Pp, double* packed, vmcpde_stream stream);
+int vmcpde_unpack_upper_tiles(const double* packed, int32_t Pp, double* S, vmcpde_stream stream);
+int vmcpde_allreduce_sum(void* nccl_comm, double* buf, int64_t count, vmcpde_stream stream);
+int vmcpde_allreduce_moments(void* nccl_comm, double* const* mats, int32_t n_mats, int32_t Pp, double* tail, int64_t n_tail,
+                             double* packed, vmcpde_stream stream);
+/* communicator plumbing for hosts that have none: 128-byte id (host memory) from rank 0, shipped out of band */
+int vmcpde_nccl_unique_id(char* id128);
+int vmcpde_nccl_comm_init(int32_t n_ranks, int32_t rank, const char* id128, void** comm_out);
+int vmcpde_nccl_comm_destroy(void* comm);
 /* One launch of a register-resident DMMA.8x8x4 loop (148 x 4 CTAs x 8 warps): the FP64 tensor-pipe probe that gives the
  * roofline denominator of the S build (MEASURED_PEAKS.json has no FP64 entry).  `scratch`: 8 bytes of device memory.
  * *flops = floating-point operations of the launch; the caller times it with events on `stream`.  No allocation, no sync. */

@@ -35,6 +35,33 @@ lazy_diffs = {"S0": mx(T.S0, T2.S0), "F0": mx(T.F0, T2.F0), "ev": mx(T.ev, T2.ev
               "refl": mx(T._Swork, T2._Swork), "rhoVar": mx(T.rhoVar, T2.rhoVar), "CEO": mx(T._mats(vs.net.handle.Pp)[2], T2._mats(vs.net.handle.Pp)[2])}
 fp = torch.stack([T.ev.sum(), T.ev[-1], T.ev[0], upd.norm(), T.VtF.norm(), T.snr.norm(), T.invEv.sum(), T.solverResidual, T.tdvp_error,
                   info["entropy"], info["max_grad"], V.abs().sum()]).to(torch.float64)
+# the C-ABI's own NCCL entry points (for hosts without torch.distributed) against torch.distributed on the same data
+nccl_dev = 0.0
+if world > 1:
+    import ctypes as C
+    from vmc_pde_b200 import _lib
+    L = _lib.load()
+    ident = C.create_string_buffer(128)
+    if rank == 0:
+        _lib.check(L.vmcpde_nccl_unique_id(ident))
+    box = [ident.raw if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    ident = C.create_string_buffer(box[0], 128)
+    comm = C.c_void_p()
+    _lib.check(L.vmcpde_nccl_comm_init(world, rank, ident, C.byref(comm)))
+    Pq = 256
+    g = torch.Generator(device="cuda"); g.manual_seed(100 + rank)
+    mats = [torch.randn(Pq, Pq, device="cuda", dtype=torch.float64, generator=g) for _ in range(3)]
+    tail = torch.randn(Pq + 8, device="cuda", dtype=torch.float64, generator=g)
+    ref = [m.clone() for m in mats] + [tail.clone()]
+    for t in ref:
+        dist.all_reduce(t)
+    pk = torch.empty(3 * L.vmcpde_packed_tiles_len(Pq) + Pq + 8, device="cuda", dtype=torch.float64)
+    _lib.check(L.vmcpde_allreduce_moments(comm, _lib.ptr_array(mats), 3, Pq, _lib.ptr(tail), Pq + 8, _lib.ptr(pk), _lib.stream()))
+    torch.cuda.synchronize()
+    nccl_dev = max(float((torch.triu(a) - torch.triu(b)).abs().max()) for a, b in zip(mats, ref[:3]))
+    nccl_dev = max(nccl_dev, float((tail - ref[3]).abs().max()))
+    _lib.check(L.vmcpde_nccl_comm_destroy(comm))
 fps = [fp]
 if world > 1:
     fps = [torch.empty_like(fp) for _ in range(world)]
@@ -43,6 +70,6 @@ if rank == 0:
     torch.save({"update": upd.cpu(), "S0": T.S0.cpu(), "F0": T.F0.cpu(), "ev": T.ev.cpu(), "VtF": T.VtF.cpu(), "snr": T.snr.cpu(),
                 "res": T.solverResidual.cpu(), "err": T.tdvp_error.cpu(), "V": V.cpu(), "entropy": info["entropy"].cpu(),
                 "covar": info["covar"].cpu(), "q_eager": q_eager, "q_lazy": q_lazy, "upd_lazy": upd2.cpu(), "SExp": T.SExp.cpu(),
-                "fingerprints": torch.stack(fps).cpu(), "partition": part, "lazy_diffs": lazy_diffs}, args.out)
+                "fingerprints": torch.stack(fps).cpu(), "partition": part, "lazy_diffs": lazy_diffs, "nccl_dev": nccl_dev}, args.out)
 if world > 1:
     dist.barrier(); dist.destroy_process_group()

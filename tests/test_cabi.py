@@ -102,3 +102,18 @@ def test_loader_fails_loudly_when_library_missing(tmp_path, monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "libvmcpde.so"))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         _lib.load()
+
+
+@pytest.mark.gpu
+def test_torch_free_c_caller():
+    """tests/cabi_smoke.cu: a plain C++/CUDA program (cudaMalloc, default stream, no torch, no Python) drives one right-hand side
+    through the C-ABI -- sample -> local terms -> moments -> centring -> Gram (DMMA and tcgen05 split) -> eigh -> solve tail --
+    and the two-call eigensolver; "raw pointers + stream, caller-owned workspaces" demonstrated, not asserted."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cabi_smoke")
+    if not os.path.exists(exe):
+        subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-o", exe, exe + ".cu",
+                               "-L" + os.path.join(root, "vmc_pde_b200"), "-lvmcpde", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../vmc_pde_b200"])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "CABI_SMOKE OK" in r.stdout, r.stdout + r.stderr

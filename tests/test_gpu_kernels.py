@@ -248,6 +248,40 @@ def test_gram_split_tcgen05_within_the_stated_tolerance(L, n, P):
             assert np.abs(np.triu(got)[:, P:]).max() == 0.0      # zero padding columns stay zero
 
 
+def test_packed_tiles_and_nccl_entry_points_single_rank(L):
+    """vmcpde_pack/unpack_upper_tiles round trip (only the upper 128 x 128 tiles travel) and the NCCL entry points on a
+    one-rank communicator created through the C-ABI itself (sum over one rank = identity; 2 ranks: tests/test_gpu_multi.py)."""
+    from vmc_pde_b200 import _lib
+    f64 = torch.float64
+    Pp = 384
+    S = torch.randn(Pp, Pp, device=dev(), dtype=f64)
+    ln = L.vmcpde_packed_tiles_len(Pp)
+    assert ln == 6 * 128 * 128
+    packed = torch.zeros(ln, device=dev(), dtype=f64)
+    _lib.check(L.vmcpde_pack_upper_tiles(_lib.ptr(S), Pp, _lib.ptr(packed), _lib.stream()))
+    back = torch.full((Pp, Pp), -1.0, device=dev(), dtype=f64)
+    _lib.check(L.vmcpde_unpack_upper_tiles(_lib.ptr(packed), Pp, _lib.ptr(back), _lib.stream()))
+    for ti in range(3):
+        for tj in range(3):
+            blk = (slice(ti * 128, ti * 128 + 128), slice(tj * 128, tj * 128 + 128))
+            assert torch.equal(back[blk], S[blk]) if tj >= ti else bool((back[blk] == -1.0).all())
+    ident = C.create_string_buffer(128)
+    _lib.check(L.vmcpde_nccl_unique_id(ident))
+    comm = C.c_void_p()
+    _lib.check(L.vmcpde_nccl_comm_init(1, 0, ident, C.byref(comm)))
+    v = torch.arange(1000, device=dev(), dtype=f64)
+    _lib.check(L.vmcpde_allreduce_sum(comm, _lib.ptr(v), 1000, _lib.stream()))
+    mats = [torch.randn(Pp, Pp, device=dev(), dtype=f64) for _ in range(2)]
+    ref = [m.clone() for m in mats]
+    tail = torch.randn(Pp + 8, device=dev(), dtype=f64); tail_ref = tail.clone()
+    pk = torch.empty(2 * ln + Pp + 8, device=dev(), dtype=f64)
+    _lib.check(L.vmcpde_allreduce_moments(comm, _lib.ptr_array(mats), 2, Pp, _lib.ptr(tail), Pp + 8, _lib.ptr(pk), _lib.stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(v, torch.arange(1000, device=dev(), dtype=f64)) and torch.equal(tail, tail_ref)
+    assert all(torch.equal(torch.triu(a), torch.triu(b)) for a, b in zip(mats, ref))
+    _lib.check(L.vmcpde_nccl_comm_destroy(comm))
+
+
 def _eigh(L, S_np):
     from vmc_pde_b200 import _lib
     n = S_np.shape[0]; ld = L.vmcpde_padded_params(n)

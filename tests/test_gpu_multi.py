@@ -53,5 +53,6 @@ def test_sharded_and_pipelined_rhs_match_the_single_gpu_result(tmp_path):
             else:                 # one launch for all matrices: the K-split of its last round depends on their number
                 dl = b["upd_lazy"] - b["update"]
                 assert float(dl @ a["S0"] @ dl) <= 1e-14 * float(a["update"] @ a["S0"] @ a["update"]), b["lazy_diffs"]
+            assert b["nccl_dev"] < 1e-12       # vmcpde_allreduce_moments (packed tiles, own communicator) == torch.distributed
             fps = b["fingerprints"]
             assert fps.shape[0] == world and all(torch.equal(fps[r], fps[0]) for r in range(world))      # bit-identical on every rank

@@ -211,6 +211,21 @@ def gram_split(O, n, ldo, Pp, weight, S):
                                    _lib.stream()))
 
 
+def packed_tiles_len(Pp):
+    return int(_lib.load().vmcpde_packed_tiles_len(int(Pp)))
+
+
+def pack_upper(S, Pp, packed):
+    """Upper-triangular 128 x 128 tiles of S (Pp x Pp) -> contiguous `packed` (what crosses NVLink in the all-reduce)."""
+    _count(1)
+    _lib.check(_lib.load().vmcpde_pack_upper_tiles(_lib.ptr(S), int(Pp), _lib.ptr(packed), _lib.stream()))
+
+
+def unpack_upper(packed, Pp, S):
+    _count(1)
+    _lib.check(_lib.load().vmcpde_unpack_upper_tiles(_lib.ptr(packed), int(Pp), _lib.ptr(S), _lib.stream()))
+
+
 def sym_finalize(S, Pp, scale):
     _count(1)
     _lib.check(_lib.load().vmcpde_sym_finalize(_lib.ptr(S), int(Pp), float(scale), _lib.stream()))

@@ -37,6 +37,14 @@ SIGNATURES = {
     "vmcpde_gram": (C.c_int, [_vp, _i64, _i64, _i32, _i32, C.POINTER(_vp), C.POINTER(_vp), _vp]),
     "vmcpde_gram_split_workspace_bytes": (C.c_int, [_i64, _i32, C.POINTER(C.c_size_t)]),
     "vmcpde_gram_split": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "vmcpde_packed_tiles_len": (_i64, [_i32]),
+    "vmcpde_pack_upper_tiles": (C.c_int, [_vp, _i32, _vp, _vp]),
+    "vmcpde_unpack_upper_tiles": (C.c_int, [_vp, _i32, _vp, _vp]),
+    "vmcpde_allreduce_sum": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "vmcpde_allreduce_moments": (C.c_int, [_vp, C.POINTER(_vp), _i32, _i32, _vp, _i64, _vp, _vp]),
+    "vmcpde_nccl_unique_id": (C.c_int, [C.c_char_p]),
+    "vmcpde_nccl_comm_init": (C.c_int, [_i32, _i32, C.c_char_p, C.POINTER(_vp)]),
+    "vmcpde_nccl_comm_destroy": (C.c_int, [_vp]),
     "vmcpde_sym_finalize": (C.c_int, [_vp, _i32, _dbl, _vp]),
     "vmcpde_diag_shift": (C.c_int, [_vp, _vp, _i32, _i32, _dbl, _vp]),
     "vmcpde_dmma_probe": (C.c_int, [_vp, _i32, C.POINTER(_dbl), _vp]),

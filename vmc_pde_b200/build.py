@@ -20,7 +20,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 EXTRA = os.environ.get("VMCPDE_NVCC_EXTRA", "").split()
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"] + EXTRA
-PLAIN = ["capi.cu", "gram.cu", "gram_split.cu", "reduce_kernels.cu", "solve.cu", "eigh.cu", "eigh_blocked.cu", "observables.cu", "particles.cu"]
+PLAIN = ["capi.cu", "gram.cu", "gram_split.cu", "reduce_kernels.cu", "solve.cu", "eigh.cu", "eigh_blocked.cu", "observables.cu", "particles.cu", "collectives.cu"]
 
 
 def _units():

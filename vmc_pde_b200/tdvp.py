@@ -92,7 +92,7 @@ class LazyGram:
 
 # seconds of the serial eigensolver stages (tridiagonalisation + divide & conquer) on one B200 by matrix size, measured with
 # bench.py / tools/probe_eigh.py (profiles/); log-log interpolation in between
-_SOLVER_SECONDS = ((384, 0.008), (1024, 0.022), (2053, 0.050), (4096, 0.12), (8187, 0.33), (12000, 0.85), (16385, 2.45), (25600, 9.0))
+_SOLVER_SECONDS = ((384, 0.006), (1024, 0.015), (2053, 0.030), (4096, 0.080), (8187, 0.33), (12000, 0.85), (16385, 2.8), (25600, 10.0))
 
 
 def solver_seconds(P):
@@ -228,14 +228,15 @@ class TDVP:
         back-transformation -- the serial stages leave the critical path of every rank but one."""
         S0, SExp, CEO, Fsum, var_sum = self._mats(Pp)
         head = Pp * Pp + Pp + 8
-        if pipeline is None:
-            mpi.allreduce_(self._second)
-        else:
-            mpi.allreduce_(self._second[:head])
-        inv = 1.0 / N
-        _kernels.sym_finalize(S0, Pp, inv)
+        R, rank = mpi.comm.Get_size(), mpi.comm.Get_rank()
         eager_sexp = self.computeSExp is True or (self.computeSExp and not self._lazy_ok)
         use_ceo = self.computeSNR and self.solver == "eigh"
+        rest_mats = ([SExp] if eager_sexp else []) + ([CEO] if use_ceo else [])
+        if R > 1:
+            # only the upper-triangular tiles are computed, so only they cross NVLink (SURVEY 8e: packed upper triangles)
+            self._allreduce_packed([S0] + ([] if pipeline is not None else rest_mats), Pp, self._second[Pp * Pp:head])
+        inv = 1.0 / N
+        _kernels.sym_finalize(S0, Pp, inv)
         F = Fsum * inv
         self.ElocVar = (var_sum[0] * inv).clone()
         # S0 / SExp / S (P x P, 0.5 GB each at P = 8187) are views of the persistent buffers: valid until the next call
@@ -250,7 +251,6 @@ class TDVP:
         meanE2 = float(first[2]) * inv  # mean(Eloc**2) of the un-centred local term (tdvp.py:93); host scalar
         ev, VtF, rhoVar, snr, invEv, update, w0, w1 = [self._vecs[i] for i in range(8)]
         self._Swork.copy_(S)
-        R, rank = mpi.comm.Get_size(), mpi.comm.Get_rank()
         if pipeline is not None:
             ws = _kernels.workspace(_kernels.eigh_workspace_bytes(P, Pp))
             if self._ZT is None:
@@ -259,7 +259,7 @@ class TDVP:
                 _kernels.eigh_factor(self._Swork, P, Pp, ev, self._ZT, self._tau[:Pp], ws)
                 self._tau[Pp:].copy_(ev)
             pipeline()
-            mpi.allreduce_(self._second[head:])
+            self._allreduce_packed(rest_mats, Pp, None)
             mpi.broadcast_(self._Swork, self.solverRank)        # the reflectors
             mpi.broadcast_(self._ZT, self.solverRank)           # eigenvectors of the tridiagonal matrix (rows)
             mpi.broadcast_(self._tau, self.solverRank)          # tau | ev
@@ -322,6 +322,27 @@ class TDVP:
         self.solverResidual, self.tdvp_error = self._scal[0].clone(), self._scal[1].clone()
         return update[:P].clone()
 
+    def _allreduce_packed(self, mats, Pp, tail):
+        """SUM over ranks of the upper tiles of `mats` (+ the `tail` vector) with one all-reduce of the packed buffer."""
+        if not mats and tail is None:
+            return
+        ln = _kernels.packed_tiles_len(Pp)
+        n_tail = 0 if tail is None else tail.numel()
+        need = len(mats) * ln + n_tail
+        if getattr(self, "_packed", None) is None or self._packed.numel() < need:
+            self._packed = None
+            self._packed = _kernels.empty(3 * ln + Pp + 8)
+        buf = self._packed[:need]
+        for m, M in enumerate(mats):
+            _kernels.pack_upper(M, Pp, buf[m * ln:(m + 1) * ln])
+        if n_tail:
+            buf[len(mats) * ln:].copy_(tail)
+        mpi.allreduce_(buf)
+        for m, M in enumerate(mats):
+            _kernels.unpack_upper(buf[m * ln:(m + 1) * ln], Pp, M)
+        if n_tail:
+            tail.copy_(buf[len(mats) * ln:])
+
     # ---- sample partition of the fused path -----------------------------------------------------------
     def _pipelined(self, R, P, Pp):
         """The solver-rank pipeline applies to a multi-rank eigen-solve on the blocked path with a sharded back-transformation."""
@@ -342,8 +363,11 @@ class TDVP:
         if self.solverShare is not None:
             n0 = int(max(0.0, min(1.0, float(self.solverShare))) * N / R)
         else:
-            g = 3.0 * P * (P + 1.0) / 34.5e12                      # DMMA Gram rate measured on B200
-            delta = 1.5 * solver_seconds(P) / g
+            # seconds per sample of the Grams that overlap the serial stages (SExp, C_EO): FP64 DMMA at 34.5 TFLOP/s, or the
+            # tcgen05 split path at 150 TFLOP/s FP64-equivalent (rates measured on B200)
+            n_rest = (1 if (self.computeSExp is True) else 0) + (1 if self.computeSNR else 0)
+            g_rest = n_rest * P * (P + 1.0) / (150e12 if self.gramPrecision == "split" else 34.5e12)
+            delta = solver_seconds(P) / g_rest if g_rest > 0 else float("inf")
             n0 = int(max(0.0, (N - (R - 1) * delta) / R))
         n0 = min(n0 // 16 * 16, N)
         others = R - 1
