@@ -152,14 +152,18 @@ __device__ __forceinline__ void sp_decode(long long p, int tiles, int G, int& ti
 
 // ------------------------------------------------------------------------------------------------ pre-pass
 // X[(slice * Pp + c) * n_pad + s] = slice-th bf16 term of sqrt(w[s]) * O[s][c]; zero for s >= n.
+// One block: 64 columns x 256 samples (reads 512-byte row pieces, writes 512-byte runs of samples; the first version with
+// 64 samples per block wrote 128-byte runs and reached 2.8 TB/s).
+constexpr int kSplitRows = 256;
 __global__ void __launch_bounds__(256) split_rows_kernel(const double* __restrict__ O, long long n, long long ldo, int Pp,
                                                          const double* __restrict__ w, long long n_pad,
                                                          __nv_bfloat16* __restrict__ X) {
-  __shared__ __nv_bfloat16 t[3][64][66];   // [slice][column][sample], padded against bank conflicts
-  const long long s0 = (long long)blockIdx.x * 64;
+  extern __shared__ __nv_bfloat16 sp_t[];                      // [3][64][kSplitRows + 2]
+  constexpr int LD = kSplitRows + 2;
+  const long long s0 = (long long)blockIdx.x * kSplitRows;
   const int c0 = blockIdx.y * 64;
-  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;   // tx: column inside the tile, ty: sample sub-row
-  for (int i = ty; i < 64; i += 4) {
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;     // tx: column inside the tile, ty: sample sub-row
+  for (int i = ty; i < kSplitRows; i += 4) {
     const long long s = s0 + i;
     double x = 0.0;
     if (s < n) {
@@ -171,15 +175,19 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const double* __restric
     const __nv_bfloat16 a2 = __float2bfloat16_rn((float)r1);
     const double r2 = r1 - (double)__bfloat162float(a2);
     const __nv_bfloat16 a3 = __float2bfloat16_rn((float)r2);
-    t[0][tx][i] = a1; t[1][tx][i] = a2; t[2][tx][i] = a3;
+    sp_t[(0 * 64 + tx) * LD + i] = a1; sp_t[(1 * 64 + tx) * LD + i] = a2; sp_t[(2 * 64 + tx) * LD + i] = a3;
   }
   __syncthreads();
-  // 3 x 64 rows of 64 samples (128 B): one warp per row, 2 samples (4 B) per lane
+  // 3 x 64 rows of 256 samples (512 B): one warp per row, 4 x 2 samples (4 B) per lane
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int row = warp; row < 192; row += 8) {
-    const int sl = row >> 6, c = row & 63;
-    const uint32_t v = *reinterpret_cast<const uint32_t*>(&t[sl][c][2 * lane]);
-    *reinterpret_cast<uint32_t*>(&X[((long long)sl * Pp + c0 + c) * n_pad + s0 + 2 * lane]) = v;
+    const int c = row & 63, sl = row >> 6;
+    __nv_bfloat16* dst = X + ((long long)sl * Pp + c0 + c) * n_pad + s0;
+#pragma unroll
+    for (int j = 0; j < kSplitRows / 64; ++j) {
+      const uint32_t v = *reinterpret_cast<const uint32_t*>(&sp_t[row * LD + 64 * j + 2 * lane]);
+      *reinterpret_cast<uint32_t*>(dst + 64 * j + 2 * lane) = v;
+    }
   }
 }
 
@@ -377,7 +385,13 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_gram_split(const do
   VMC_REQUIRE((long long)3 * Pp < (1ll << 31) && n_pad < (1ll << 31), "vmcpde_gram_split: problem too large for one tensor map");
   cudaStream_t s = (cudaStream_t)stream;
   __nv_bfloat16* X = (__nv_bfloat16*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
-  split_rows_kernel<<<dim3((unsigned)(n_pad / 64), Pp / 64), 256, 0, s>>>(O, n, ldo, Pp, w, n_pad, X);
+  const size_t split_smem = (size_t)3 * 64 * (kSplitRows + 2) * sizeof(__nv_bfloat16);
+  static bool split_attr = false;
+  if (!split_attr) {
+    VMC_CUDA_CHECK(cudaFuncSetAttribute(split_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)split_smem));
+    split_attr = true;
+  }
+  split_rows_kernel<<<dim3((unsigned)(n_pad / kSplitRows), Pp / 64), 256, split_smem, s>>>(O, n, ldo, Pp, w, n_pad, X);
   VMC_LAUNCH_CHECK("split_rows_kernel");
   SpEncodeTiledFn enc = sp_encode_fn();
   if (!enc) return set_error(VMCPDE_ECUDA, "cuTensorMapEncodeTiled entry point not available");

@@ -349,7 +349,7 @@ class TDVP:
         return (R > 1 and self.pipelineSolve and self.solver == "eigh" and self.shardSolve and Pp // 128 >= R
                 and P >= 384 and P <= 25 * 1024)
 
-    def sample_partition(self, N, R, P):
+    def sample_partition(self, N, R, P, pipelined=None):
         """[(first, n)] per rank.  Equal contiguous shards unless the solve is pipelined: then the solver rank,
         which spends E(P) seconds in the serial stages of the eigensolver while the others build the SExp / C_EO Grams, gets
         n0 samples and the others n1 with (2/3) g (n1 - n0) = E, g = seconds of the three Grams per sample -- all ranks
@@ -358,7 +358,9 @@ class TDVP:
         base, rem = N // R, N % R
         equal = [(r * base + min(r, rem), base + (1 if r < rem else 0)) for r in range(R)]
         Pp = _kernels.round_up(P, 128)
-        if not self._pipelined(R, P, Pp):
+        if pipelined is None:
+            pipelined = self._pipelined(R, P, Pp)
+        if not pipelined:
             return equal
         if self.solverShare is not None:
             n0 = int(max(0.0, min(1.0, float(self.solverShare))) * N / R)
@@ -480,10 +482,10 @@ class TDVP:
         not drift between consecutive right-hand sides of a run (after the first call the cached O buffer no longer counts as
         free memory)."""
         plan_key = (n_local, Pp, self.chunkSamples, self.memoryFraction)
-        if getattr(self, "_plan", None) is not None and self._plan[0] == plan_key:
-            return self._plan[1]
-        self._plan = (plan_key, self._plan_chunks_now(n_local, Pp))
-        return self._plan[1]
+        plans = self.__dict__.setdefault("_plans", {})
+        if plan_key not in plans:
+            plans[plan_key] = self._plan_chunks_now(n_local, Pp)
+        return plans[plan_key]
 
     def _plan_chunks_now(self, n_local, Pp):
         free, _ = torch.cuda.mem_get_info(global_defs.device())
@@ -502,7 +504,15 @@ class TDVP:
         h = psi.net.handle
         P, Pp, d = h.P, h.Pp, h.dim
         R, rank = mpi.comm.Get_size(), mpi.comm.Get_rank()
-        first_idx, n_local = self.sample_partition(N, R, P)[rank]
+        pipelined = self._pipelined(R, P, Pp)
+        if pipelined:   # needs the whole rank-local O resident on every rank: else equal shards and the replicated solve
+            part = self.sample_partition(N, R, P, True)
+            fits = self._plan_chunks(max(n for _, n in part), Pp)[1]
+            flag = torch.tensor([0.0 if fits else 1.0], dtype=torch.float64, device=global_defs.device())
+            mpi.allreduce_(flag)
+            pipelined = bool(flag.item() == 0.0)
+        first_idx, n_local = self.sample_partition(N, R, P, pipelined)[rank]
+        self._last_partition = (pipelined, first_idx, n_local)
         key = psi.sampler.next_key()                       # sampler.py:73 (one key per psi.sample call)
         chi2_all = psi.chi2_draws(n_local, first_idx, N)
         eq = evolutionEq.equation_struct(t)
@@ -552,11 +562,7 @@ class TDVP:
         toc("solve TDVP eqn.", t0)
         # pass 2: centring, force vector, weighted Grams (tdvp.py:40-47); local terms are re-evaluated chunk by chunk
         # when the whole O does not fit in memory (same key and counters -> identical samples)
-        pipelined = self._pipelined(R, P, Pp)
-        if pipelined:   # needs the whole rank-local O resident on every rank
-            flag = torch.tensor([0.0 if stored else 1.0], dtype=torch.float64, device=global_defs.device())
-            mpi.allreduce_(flag)
-            pipelined = bool(flag.item() == 0.0)
+        pipelined = pipelined and stored
         which = "s0" if pipelined else "all"
         for c0, cn in chunks:
             if cn == 0:
