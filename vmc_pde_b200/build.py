@@ -71,7 +71,35 @@ def build(force=False, verbose=True):
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
     open(stamp_file, "w").write(stamp)
+    build_xla_shim(verbose)
     return LIB
+
+
+def xla_ffi_include_dir():
+    """Directory of xla/ffi/api/ffi.h when JAX is importable (probed on every build), else None."""
+    try:
+        import jax
+        d = jax.ffi.include_dir()
+        return d if os.path.exists(os.path.join(d, "xla", "ffi", "api", "ffi.h")) else None
+    except Exception:
+        return None
+
+
+def build_xla_shim(verbose=True):
+    """libvmcpde_xla.so: the XLA-FFI handlers of csrc/xla_ffi_shim.cc (north star: thin jax.ffi custom calls).  Built only
+    when the XLA FFI headers exist; this image has no JAX, so here the function reports and returns None."""
+    inc = xla_ffi_include_dir()
+    if inc is None:
+        if verbose:
+            print("xla_ffi_shim.cc not compiled: `import jax` / jax.ffi.include_dir() unavailable in this environment", file=sys.stderr)
+        return None
+    out = os.path.join(HERE, "libvmcpde_xla.so")
+    cmd = [NVCC, "-shared", "-Xcompiler", "-fPIC", "-std=c++17", "-I" + inc, "-I" + os.path.join(HERE, "..", "include"),
+           os.path.join(CSRC, "xla_ffi_shim.cc"), "-L" + HERE, "-lvmcpde", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN", "-o", out]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("XLA-FFI shim failed to compile:\n" + r.stdout + r.stderr)
+    return out
 
 
 if __name__ == "__main__":

@@ -152,9 +152,9 @@ __device__ __forceinline__ void sp_decode(long long p, int tiles, int G, int& ti
 
 // ------------------------------------------------------------------------------------------------ pre-pass
 // X[(slice * Pp + c) * n_pad + s] = slice-th bf16 term of sqrt(w[s]) * O[s][c]; zero for s >= n.
-// One block: 64 columns x 256 samples (reads 512-byte row pieces, writes 512-byte runs of samples; the first version with
-// 64 samples per block wrote 128-byte runs and reached 2.8 TB/s).
-constexpr int kSplitRows = 256;
+// One block: 64 columns x 128 samples (reads 512-byte row pieces, writes 256-byte runs of samples, 4 blocks per SM; with
+// 64 samples per block: 10.8 ms at C3, with 256 samples and 99 KB of shared memory per block: 18 ms -- occupancy).
+constexpr int kSplitRows = 128;
 __global__ void __launch_bounds__(256) split_rows_kernel(const double* __restrict__ O, long long n, long long ldo, int Pp,
                                                          const double* __restrict__ w, long long n_pad,
                                                          __nv_bfloat16* __restrict__ X) {
@@ -163,13 +163,17 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const double* __restric
   const long long s0 = (long long)blockIdx.x * kSplitRows;
   const int c0 = blockIdx.y * 64;
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;     // tx: column inside the tile, ty: sample sub-row
+  __shared__ double sw[kSplitRows];                           // sqrt of the row weights, once per sample (not per element)
+  if (threadIdx.x < kSplitRows) {
+    const long long s = s0 + threadIdx.x;
+    sw[threadIdx.x] = (s < n) ? (w ? sqrt(w[s]) : 1.0) : 0.0;
+  }
+  __syncthreads();
+#pragma unroll 4
   for (int i = ty; i < kSplitRows; i += 4) {
     const long long s = s0 + i;
     double x = 0.0;
-    if (s < n) {
-      x = O[s * ldo + c0 + tx];
-      if (w) x *= sqrt(w[s]);
-    }
+    if (s < n) x = O[s * ldo + c0 + tx] * sw[i];
     const __nv_bfloat16 a1 = __float2bfloat16_rn((float)x);
     const double r1 = x - (double)__bfloat162float(a1);
     const __nv_bfloat16 a2 = __float2bfloat16_rn((float)r1);
@@ -178,7 +182,7 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const double* __restric
     sp_t[(0 * 64 + tx) * LD + i] = a1; sp_t[(1 * 64 + tx) * LD + i] = a2; sp_t[(2 * 64 + tx) * LD + i] = a3;
   }
   __syncthreads();
-  // 3 x 64 rows of 256 samples (512 B): one warp per row, 4 x 2 samples (4 B) per lane
+  // 3 x 64 rows of kSplitRows samples: one warp per row, 2 samples (4 B) per lane and 64-sample piece
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int row = warp; row < 192; row += 8) {
     const int c = row & 63, sl = row >> 6;
