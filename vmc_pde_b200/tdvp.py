@@ -219,7 +219,7 @@ class TDVP:
         for wgt, mat in split:
             _kernels.gram_split(O, n, ldo, Pp, wgt, mat)
 
-    def _finish(self, P, Pp, N, first, pipeline=None):
+    def _finish(self, P, Pp, N, first, pipeline=None, early=None):
         """All-reduce of the second moments, normalisation, regularised solve (tdvp.py:50-51,57-94).
 
         `pipeline` (several ranks, blocked eigensolver): a callable that launches the SExp / C_EO Grams of this rank.  Then
@@ -232,6 +232,8 @@ class TDVP:
         eager_sexp = self.computeSExp is True or (self.computeSExp and not self._lazy_ok)
         use_ceo = self.computeSNR and self.solver == "eigh"
         rest_mats = ([SExp] if eager_sexp else []) + ([CEO] if use_ceo else [])
+        if pipeline is not None and pipeline[0] > 0:
+            pipeline[1](0, pipeline[0])          # solver rank: fills its wait for the slowest S0 pass
         if R > 1:
             # only the upper-triangular tiles are computed, so only they cross NVLink (packed upper triangles)
             self._allreduce_packed([S0] + ([] if pipeline is not None else rest_mats), Pp, self._second[Pp * Pp:head])
@@ -255,10 +257,13 @@ class TDVP:
             ws = _kernels.workspace(_kernels.eigh_workspace_bytes(P, Pp))
             if self._ZT is None:
                 self._ZT, self._tau = _kernels.empty(Pp, Pp), _kernels.zeros(2 * Pp)
+            if early is not None:
+                early()       # work that does not depend on the solve (observables, with their small collectives): enqueued
+                              # on every rank BEFORE the solver rank's serial stages, i.e. off the critical path
             if rank == self.solverRank:
                 _kernels.eigh_factor(self._Swork, P, Pp, ev, self._ZT, self._tau[:Pp], ws)
                 self._tau[Pp:].copy_(ev)
-            pipeline()
+            pipeline[1](pipeline[0], pipeline[2])
             self._allreduce_packed(rest_mats, Pp, None)
             mpi.broadcast_(self._Swork, self.solverRank)        # the reflectors
             mpi.broadcast_(self._ZT, self.solverRank)           # eigenvectors of the tridiagonal matrix (rows)
@@ -349,6 +354,13 @@ class TDVP:
         return (R > 1 and self.pipelineSolve and self.solver == "eigh" and self.shardSolve and Pp // 128 >= R
                 and P >= 384 and P <= 25 * 1024)
 
+    def _gram_seconds_per_sample(self, P):
+        """(S0, SExp + C_EO) Gram seconds per sample on one B200: FP64 DMMA at 34.5 TFLOP/s, the tcgen05 split path at
+        150 TFLOP/s FP64-equivalent (measured)."""
+        n_rest = (1 if (self.computeSExp is True) else 0) + (1 if (self.computeSNR and self.solver == "eigh") else 0)
+        per = P * (P + 1.0)
+        return per / 34.5e12, n_rest * per / (150e12 if self.gramPrecision == "split" else 34.5e12)
+
     def sample_partition(self, N, R, P, pipelined=None):
         """[(first, n)] per rank.  Equal contiguous shards unless the solve is pipelined: then the solver rank,
         which spends E(P) seconds in the serial stages of the eigensolver while the others build the SExp / C_EO Grams, gets
@@ -365,12 +377,15 @@ class TDVP:
         if self.solverShare is not None:
             n0 = int(max(0.0, min(1.0, float(self.solverShare))) * N / R)
         else:
-            # seconds per sample of the Grams that overlap the serial stages (SExp, C_EO): FP64 DMMA at 34.5 TFLOP/s, or the
-            # tcgen05 split path at 150 TFLOP/s FP64-equivalent (rates measured on B200)
-            n_rest = (1 if (self.computeSExp is True) else 0) + (1 if self.computeSNR else 0)
-            g_rest = n_rest * P * (P + 1.0) / (150e12 if self.gramPrecision == "split" else 34.5e12)
-            delta = solver_seconds(P) / g_rest if g_rest > 0 else float("inf")
+            # workers: (g_s0 + g_rest) n1; solver rank: g_s0 n1 (it waits for the slowest S0, filling the wait with the
+            # SExp / C_EO Grams of its first samples) + E + the rest of its own SExp / C_EO  =>  (n1 - n0) (g_s0 + g_rest) = E
+            g_s0, g_rest = self._gram_seconds_per_sample(P)
+            delta = solver_seconds(P) / (g_s0 + g_rest)
             n0 = int(max(0.0, (N - (R - 1) * delta) / R))
+            # E dominates (many ranks): the solver rank can still take what it finishes, S0 and SExp / C_EO, inside the other
+            # ranks' S0 pass -- n0 (g_s0 + g_rest) = n1 g_s0 -- which shortens that pass for everybody
+            frac = g_s0 / (g_s0 + g_rest)
+            n0 = max(n0, int(N * frac / ((R - 1) + frac)))
         n0 = min(n0 // 16 * 16, N)
         others = R - 1
         b2, r2 = (N - n0) // others, (N - n0) % others
@@ -452,7 +467,9 @@ class TDVP:
             t0 = tic(); update, self.solverResidual, self.tdvp_error = self.solve(Eloc, sampleGradients, logProbs); toc("solve TDVP eqn.", t0)
             x_all, lp_all, E_all = sampleConfigs.reshape(-1, sampleConfigs.shape[-1]), logProbs.reshape(-1), Eloc.reshape(-1)
         else:
-            update, x_all, lp_all, E_all = self._fused_rhs(psi, evolutionEq, t, nSamplesTDVP, tic, toc)
+            self._early_info = None
+            update, x_all, lp_all, E_all = self._fused_rhs(psi, evolutionEq, t, nSamplesTDVP, tic, toc,
+                                                           obs_early=nSamplesObs if nSamplesObs <= nSamplesTDVP else None)
 
         if nSamplesObs > nSamplesTDVP:  # tdvp.py:130-134
             t0 = tic()
@@ -473,7 +490,10 @@ class TDVP:
             print("nan encountered. Exitting.")
             raise SystemExit(1)
 
-        info = self._observables(psi, x_obs, lp_obs, E_all, n_obs_glob, nSamplesObs)
+        info = getattr(self, "_early_info", None)     # pipelined multi-rank solve: already enqueued before the eigensolve
+        if info is None or not fused:
+            info = self._observables(psi, x_obs, lp_obs, E_all, n_obs_glob, nSamplesObs)
+        self._early_info = None
         return update, info
 
     def _plan_chunks(self, n_local, Pp):
@@ -500,7 +520,7 @@ class TDVP:
             return n_pad, True
         return rows, False
 
-    def _fused_rhs(self, psi, evolutionEq, t, N, tic, toc):
+    def _fused_rhs(self, psi, evolutionEq, t, N, tic, toc, obs_early=None):
         h = psi.net.handle
         P, Pp, d = h.P, h.Pp, h.dim
         R, rank = mpi.comm.Get_size(), mpi.comm.Get_rank()
@@ -577,10 +597,27 @@ class TDVP:
         self._lazy_src, self._lazy_gen = (O, n_local, _kernels.round_up(max(n_local, 1), 16), self._scratch[2]), self._gen
         rest = None
         if pipelined:
-            def rest():
-                if n_local > 0:
-                    self._pass2_chunk(E_all, lp_all, O, n_local, _kernels.round_up(n_local, 16), Pp, Pp, meanO, meanE, self._scratch, "rest")
-        update = self._finish(P, Pp, N, first, pipeline=rest)
+            n_pad_all = _kernels.round_up(max(n_local, 1), 16)
+
+            def rest_range(lo, hi):
+                """SExp / C_EO Grams of the local samples [lo, hi) (lo, and hi unless it is n_local, multiples of 16)."""
+                if hi > lo:
+                    sc = tuple(a[lo:] for a in self._scratch)
+                    self._pass2_chunk(E_all[lo:hi], lp_all[lo:hi], O[lo:], hi - lo, (n_pad_all if hi == n_local else hi) - lo, Pp, Pp,
+                                      meanO, meanE, sc, "rest")
+            # samples whose SExp / C_EO Grams the solver rank builds while it waits for the other ranks' (longer) S0 pass
+            m_head = 0
+            if rank == self.solverRank and n_local > 0:
+                g_s0, g_rest = self._gram_seconds_per_sample(P)
+                n1 = max(n for _, n in self.sample_partition(N, R, P, True))
+                if g_rest > 0 and n1 > n_local:
+                    m_head = min(n_local, int((n1 - n_local) * g_s0 / g_rest)) // 16 * 16
+            rest = (m_head, rest_range, n_local)
+        early = None
+        if pipelined and obs_early is not None:
+            def early():
+                self._early_info = self._observables(psi, x_all, lp_all, E_all, N, obs_early)
+        update = self._finish(P, Pp, N, first, pipeline=rest, early=early)
         toc("solve TDVP eqn.", t0)
         return update, x_all, lp_all, E_all
 
