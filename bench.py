@@ -183,7 +183,8 @@ def parity_report(cfg_name, values, write=False):
     tol = {"ev_max": 1e-10, "ev_sum": 1e-10, "update_S0_update": 1e-8, "F_norm": 1e-10, "tdvp_error": 1e-9, "entropy": 1e-12}
     dev = {k: abs(values[k] - ref[cfg_name][k]) / max(abs(ref[cfg_name][k]), 1e-300) for k in tol}
     dev["tdvp_error"] = abs(values["tdvp_error"] - ref[cfg_name]["tdvp_error"])     # 1 + (...) / <E^2>: an O(1) cancellation, absolute
-    return {"checked_against": "tests/golden/bench_parity.json (values of the 1-GPU run; same seeds, any rank count)",
+    return {"checked_against": "tests/golden/bench_parity.json (committed values of the smallest run that holds the config: 1 GPU for C2 / C3, "
+                               "2 GPUs with the replicated solve for C4; same seeds, any rank count)",
             "rel_dev": dev, "tolerance": tol, "ok": all(dev[k] <= tol[k] for k in tol) and values["solver_residual"] < 1e-8,
             "values": values}
 
