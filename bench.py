@@ -425,7 +425,7 @@ def run_ours(args):
         line["variants"] = {"lazy_SExp_steps_per_s": 1e3 / ms_lazy, "cholesky_shift1e-4_steps_per_s": 1e3 / ms_chol,
                             "split_precision_steps_per_s": 1e3 / ms_split,
                             "split_precision": {"what": "TDVP(gramPrecision='split'): SExp and the SNR covariance on tcgen05 (bf16 x 3 split operands, "
-                                                        "6 products per logical product, FP32 TMEM accumulation over 256 samples, FP64 sums; stated "
+                                                        "6 products per logical product, FP32 TMEM accumulation over 128 samples, FP64 sums; stated "
                                                         "tolerance 1e-6); S0 on FP64 DMMA; theta_dot bit-identical to the FP64 run",
                                                 "kernel": "gram_split_kernel (rank 0)", **sk,
                                                 "roofline": {"bound": "tensor", "achieved": sk.get("bf16_tflops"), "peak": bf16_peak, "unit": "TFLOP/s",

@@ -166,9 +166,9 @@ int vmcpde_syrk_tn(const double* X, int64_t ldx, double* Out, int64_t ldo, int32
 /* Split-precision variant of vmcpde_gram for ONE matrix on the 5th-generation tensor cores (tcgen05.mma, TMEM accumulators;
  * the north star's "FP32-split path with stated tolerance"): S (ld = Pp, upper-triangular 128x128 tiles) += O^T diag(w) O with
  * every FP64 operand sqrt(w_row) * O split into three bfloat16 slices, the six slice products with i + j <= 4 accumulated in
- * FP32 in TMEM over at most 256 samples and added in FP64.  Stated tolerance: 1e-6 relative to sqrt(S_ii S_jj).  Meant for
+ * FP32 in TMEM over at most 128 samples and added in FP64.  Stated tolerance: 1e-6 relative to sqrt(S_ii S_jj).  Meant for
  * SExp (tdvp.py:47) and the SNR covariance (tdvp.py:68-70); S0 stays on vmcpde_gram.  O [n][ldo] row-major, w[n] >= 0 or
- * NULL; workspace (vmcpde_gram_split_workspace_bytes) holds the bf16 slices (3 * Pp * round_up(n, 256) * 2 bytes). */
+ * NULL; workspace (vmcpde_gram_split_workspace_bytes) holds the bf16 slices (3 * Pp * round_up(n, 128) * 2 bytes). */
 int vmcpde_gram_split_workspace_bytes(int64_t n, int32_t Pp, size_t* bytes);
 int vmcpde_gram_split(const double* O, int64_t n, int64_t ldo, int32_t Pp, const double* w, double* S, void* workspace,
                       size_t workspace_bytes, vmcpde_stream stream);

@@ -7,9 +7,10 @@
 //
 // tcgen05.mma has no FP64 kind, so an FP64 operand x (already multiplied by sqrt(w_row)) is split into three bfloat16
 // slices x = x1 + x2 + x3 + O(2^-24 |x|) and a logical product a*b becomes the six products a_i b_j with i + j <= 4,
-// accumulated in FP32 in TMEM in TWO accumulators (a1 b1, and the five small products) for at most 256 samples, then added
-// in FP64 registers by the epilogue warps.  Error of the result: <= ~4e-7 relative to sqrt(S_ii S_jj) even if the tensor
-// core truncates its FP32 accumulation (2e-8 if it rounds; NumPy emulation in DESIGN.md) -- the stated tolerance is 1e-6.
+// accumulated in FP32 in TMEM in TWO accumulators (a1 b1, and the five small products) for at most 128 samples, then added
+// in FP64 registers by the epilogue warps.  Error of the result, measured on B200: 2.2e-7 relative to sqrt(S_ii S_jj)
+// (5.0e-7 with 256-sample chunks: the tensor core truncates its FP32 accumulation, so the error grows linearly with the
+// chunk; a NumPy emulation gives 9e-9 for round-to-nearest accumulation) -- the stated tolerance is 1e-6.
 //
 //  * pre-pass (split_rows_kernel): O [n][ldo] FP64 -> X [3 slices][Pp columns][n_pad samples] bf16, sample index
 //    contiguous, so every operand tile is the canonical K-major 64-byte-swizzle UMMA layout and one TMA 2-D box
@@ -30,7 +31,7 @@
 namespace vmc {
 
 constexpr int kSpBK = 32;                 // samples per pipeline stage (64 bytes of bf16: one row of the 64-byte swizzle)
-constexpr int kSpChunk = 256;             // samples per TMEM accumulation chunk (FP32 accumulation length)
+constexpr int kSpChunk = 128;             // samples per TMEM accumulation chunk (FP32 accumulation length)
 constexpr int kSpTileBytes = 128 * kSpBK * 2;     // one slice of one operand tile: 128 columns x 32 samples x 2 B = 8 KB
 constexpr int kSpStageBytes = 6 * kSpTileBytes;   // A x 3 slices, B x 3 slices = 48 KB
 constexpr int kSpStages = 4;              // (2 stages of 64 samples left the tensor pipe 64 % busy: a freed slot was refilled
