@@ -333,7 +333,7 @@ def run_ours(args):
         sp_ms = sum(a_.elapsed_time(b_) for a_, b_, _ in split_ev)
         Pp_ = _kernels.round_up(P, 128)
         tl_ = Pp_ // 128
-        sp_flops = sum(tl_ * (tl_ + 1) / 2 * 128 * 128 * ((n_ + 255) // 256 * 256) * 2.0 * 6 for _, _, n_ in split_ev)
+        sp_flops = sum(tl_ * (tl_ + 1) / 2 * 128 * 128 * ((n_ + 127) // 128 * 128) * 2.0 * 6 for _, _, n_ in split_ev)
         variants["split_kernel"] = {"launches": len(split_ev), "ms_per_launch": sp_ms / max(len(split_ev), 1),
                                     "bf16_tflops": sp_flops / (sp_ms * 1e-3) * 1e-12 if sp_ms else None,
                                     "fp64_equivalent_tflops": sum(n_ * P * (P + 1.0) for _, _, n_ in split_ev) / (sp_ms * 1e-3) * 1e-12 if sp_ms else None}

@@ -28,7 +28,7 @@ for name, fn in (("split", lambda: _kernels.gram_split(O, n, Pp, Pp, w, S1)), ("
     res[name + "_ms"] = ms
     res[name + "_fp64_equiv_tflops"] = n * P * (P + 1.0) / (ms * 1e-3) * 1e-12
 tiles = Pp // 128
-res["split_bf16_tflops"] = tiles * (tiles + 1) / 2 * 128 * 128 * ((n + 255) // 256 * 256) * 2.0 * 6 / (res["split_ms"] * 1e-3) * 1e-12   # executed bf16 flops
+res["split_bf16_tflops"] = tiles * (tiles + 1) / 2 * 128 * 128 * ((n + 127) // 128 * 128) * 2.0 * 6 / (res["split_ms"] * 1e-3) * 1e-12   # executed bf16 flops
 d = torch.sqrt(torch.diagonal(S2)[:P])
 iu = torch.triu_indices(P, P, device="cuda")
 err = ((S1 - S2)[:P, :P][iu[0], iu[1]].abs() / (d[iu[0]] * d[iu[1]])).max()
