@@ -1,5 +1,5 @@
 // tcgen05.mma issue-rate probe: one CTA per SM issues MMAs from (zeroed) shared memory, no loads.
-// usage: utc_rate <kind: 0 bf16 128x128x16 | 1 i8 128x64x32 | 2 i8 128x128x32 | 3 i8 128x256x32> <collector 0/1> [iters]
+// usage: utc_rate <kind: 0 bf16 128x128x16 | 1 i8 128x64x32 | 2 i8 128x128x32 | 3 i8 128x256x32 | 4 bf16 128x256x16> <collector 0/1> [iters]
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -10,7 +10,7 @@ __device__ __forceinline__ uint64_t desc(uint32_t addr, uint32_t sbo16, uint64_t
 }
 template <int KIND, int COLL>
 __device__ __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
-  if constexpr (KIND == 0) {
+  if constexpr (KIND == 0 || KIND == 4) {
     if constexpr (COLL == 1) asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n}\n" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
     else if constexpr (COLL == 2) asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16.collector::a::use [%0], %1, %2, %3, p;\n}\n" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
     else asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
@@ -41,19 +41,20 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int iters, int coll, unsig
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tm = slot;
   constexpr int N = KIND == 0 ? 128 : (KIND == 1 ? 64 : (KIND == 2 ? 128 : 256));
+  constexpr bool BF = KIND == 0 || KIND == 4;
   // K-major rows of 32 bytes (one UMMA K step: 16 bf16 or 32 int8), 32-byte swizzle: 8-row atoms of 256 B
-  const uint32_t idesc = KIND == 0 ? ((1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | (8u << 24))
+  const uint32_t idesc = BF ? ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | (8u << 24))
                                    : ((2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | (8u << 24));
   if (threadIdx.x == 0) {
     const long long t0 = clock64();
     uint32_t phase = 0;
     for (int it = 0; it < iters; ++it) {
       // 8 A tiles (4 KB each) and 8 B tiles: slices p, q; 36 products p + q <= 7 into 8 accumulators (or 6 products for bf16)
-      if (KIND == 0) {
+      if (BF) {
         for (int p = 0; p < 3; ++p)
           for (int q = 0; q < 3 - p; ++q) {
-            const uint64_t a = desc(su32(smem) + p * 4096, 16, 6), b = desc(su32(smem) + 32768 + q * 4096, 16, 6);
-            const uint32_t d = tm + (p + q == 0 ? 0 : 128);
+            const uint64_t a = desc(su32(smem) + p * 4096, 16, 6), b = desc(su32(smem) + 32768 + q * (N * 32), 16, 6);
+            const uint32_t d = tm + (p + q == 0 ? 0 : N);
             if (coll && q == 0 && p < 2) mma<KIND, 1>(d, a, b, idesc, 1); else if (coll && q + 1 < 3 - p) mma<KIND, 2>(d, a, b, idesc, 1); else mma<KIND, 0>(d, a, b, idesc, 1);
           }
       } else {
@@ -88,6 +89,7 @@ int main(int argc, char** argv) {
     if (kind == 1) { cudaFuncSetAttribute(rate_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); rate_kernel<1><<<sms, 128, smem>>>(it, coll, cyc); }
     if (kind == 2) { cudaFuncSetAttribute(rate_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); rate_kernel<2><<<sms, 128, smem>>>(it, coll, cyc); }
     if (kind == 3) { cudaFuncSetAttribute(rate_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); rate_kernel<3><<<sms, 128, smem>>>(it, coll, cyc); }
+    if (kind == 4) { cudaFuncSetAttribute(rate_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); rate_kernel<4><<<sms, 128, smem>>>(it, coll, cyc); }
   };
   launch(2000);
   cudaDeviceSynchronize();
@@ -96,7 +98,8 @@ int main(int argc, char** argv) {
   float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
   unsigned long long h = 0; cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
   const int N = kind == 0 ? 128 : (kind == 1 ? 64 : (kind == 2 ? 128 : 256));
-  const double mmas = (kind == 0 ? 6.0 : 36.0) * iters, ops = mmas * 2.0 * 128 * N * (kind == 0 ? 16 : 32) * sms;
+  const bool bf = kind == 0 || kind == 4;
+  const double mmas = (bf ? 6.0 : 36.0) * iters, ops = mmas * 2.0 * 128 * N * (bf ? 16 : 32) * sms;
   printf("{\"kind\": %d, \"N\": %d, \"collector\": %d, \"ms\": %.3f, \"clk_per_mma\": %.1f, \"tops\": %.1f, \"err\": \"%s\"}\n", kind, N, coll, ms, (double)h / mmas,
          ops / (ms * 1e-3) * 1e-12, cudaGetErrorString(cudaGetLastError()));
   return 0;
