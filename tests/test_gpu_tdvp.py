@@ -415,3 +415,33 @@ def test_split_precision_grams_leave_the_update_untouched():
     assert float((b[4][big] / a[4][big] - 1).abs().max()) < 1e-3
     with pytest.raises(ValueError):
         tdvp.TDVP(gramPrecision="fp16")
+
+
+def test_checkpoint_resume_is_bit_identical(tmp_path):
+    """util.save_checkpoint / load_checkpoint (parameters, sampler key, time, stepper dt, histories): a run resumed from the
+    checkpoint in a fresh VarState continues bit for bit like the uninterrupted one (exact samplers: the key is the whole
+    RNG state, sampler.py:72-73)."""
+    from vmc_pde_b200 import tdvp, stepper, util
+    def fresh():
+        smp, vs, eq, spec = build(2, 4, 1, "no_add", "Gauss", "diffusion", np.zeros(2))
+        return vs, eq, stepper.FixedStepper(timeStep=1e-3, mode='Heun', maxStep=1e-2, increase_fac=1.3), tdvp.TDVP()
+    def advance(vs, eq, st, T, t, k, infos):
+        for _ in range(k):
+            dp, dt, info = st.step(0, T, vs.get_parameters(), evolutionEq=eq, psi=vs, nSamplesTDVP=3000, nSamplesObs=3000,
+                                   normFunction=norm_fun, timings=None)
+            vs.set_parameters(dp)
+            infos.setdefault("times", []).append(t); infos.setdefault("entropy", []).append(info["entropy"]); infos.setdefault("ev", []).append(T.ev)
+            t += dt
+        return t
+    vs, eq, st, T = fresh()
+    infos = {}
+    t = advance(vs, eq, st, T, 0.0, 3, infos)
+    ck = str(tmp_path / "checkpoint.hdf5")
+    util.save_checkpoint(ck, vs, t, st, infos)
+    t_full = advance(vs, eq, st, T, t, 3, infos)
+    vs2, eq2, st2, T2 = fresh()
+    t2, infos2 = util.load_checkpoint(ck, vs2, st2)
+    assert t2 == t and len(infos2["times"]) == 3 and np.array_equal(np.asarray(infos2["ev"][2]), infos["ev"][2].cpu().numpy())
+    t2 = advance(vs2, eq2, st2, T2, t2, 3, infos2)
+    assert t2 == t_full and torch.equal(vs2.get_parameters(), vs.get_parameters())
+    assert float(infos2["entropy"][-1]) == float(infos["entropy"][-1])

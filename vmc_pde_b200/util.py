@@ -51,6 +51,33 @@ def load_infos(wdir, name="infos.hdf5"):
         return {k: np.array(f[k]) for k in f.keys()}
 
 
+def save_checkpoint(path, vState, t, stepper=None, infos=None):
+    """Everything a run needs to continue bit for bit (the reference has no checkpoints): the flat
+    parameter vector, the sampler key (the only RNG state of the exact samplers), the time and the stepper's dt, written as
+    one flat-group HDF5 file next to infos.hdf5.  `infos` (the driver's history dict) is stored under "infos.<key>" names."""
+    data = {"parameters": vState.get_parameters().detach().cpu().numpy(), "sampler_key": np.asarray(vState.sampler.key, dtype=np.uint32),
+            "time": np.float64(t)}
+    if stepper is not None:
+        data["stepper_dt"] = np.float64(stepper.dt)
+    if infos:
+        for k, vals in infos.items():
+            data["infos." + k] = np.asarray([v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v) for v in vals])
+    from . import _hdf5
+    _hdf5.write(path, data)
+
+
+def load_checkpoint(path, vState, stepper=None):
+    """Restores what save_checkpoint wrote into `vState` (parameters, sampler key) and `stepper` (dt); returns (t, infos)."""
+    from . import _hdf5
+    d = _hdf5.read(path)
+    vState.set_parameters(torch.as_tensor(d["parameters"]))
+    vState.sampler.key = d["sampler_key"].astype(np.uint32)
+    if stepper is not None and "stepper_dt" in d:
+        stepper.dt = float(d["stepper_dt"])
+    infos = {k[len("infos."):]: list(v) for k, v in d.items() if k.startswith("infos.")}
+    return float(d["time"]), infos
+
+
 class Timings():
     """util.py:35-52."""
 
