@@ -222,10 +222,12 @@ class TDVP:
     def _finish(self, P, Pp, N, first, pipeline=None, early=None):
         """All-reduce of the second moments, normalisation, regularised solve (tdvp.py:50-51,57-94).
 
-        `pipeline` (several ranks, blocked eigensolver): a callable that launches the SExp / C_EO Grams of this rank.  Then
-        the S0 block is all-reduced first, the solver rank runs the serial stages of the eigensolver (tridiagonalisation,
-        divide & conquer) while the other ranks build those Grams, and the factors are broadcast for the sharded
-        back-transformation -- the serial stages leave the critical path of every rank but one."""
+        `pipeline` (several ranks, blocked eigensolver) = (m_head, fn, n_local) with fn(lo, hi) launching the SExp / C_EO Grams
+        of the local samples [lo, hi).  Then the S0 block is all-reduced first (the solver rank fills its wait for it with
+        fn(0, m_head)), the solver rank runs the serial stages of the eigensolver (tridiagonalisation, divide & conquer) while
+        the other ranks build those Grams, and the factors are broadcast for the sharded back-transformation -- the serial
+        stages leave the critical path of every rank but one.  `early`: enqueued on every rank right
+        before those serial stages (the observables block, which does not depend on the solve)."""
         S0, SExp, CEO, Fsum, var_sum = self._mats(Pp)
         head = Pp * Pp + Pp + 8
         R, rank = mpi.comm.Get_size(), mpi.comm.Get_rank()
