@@ -44,13 +44,15 @@ enum {
 typedef struct vmcpde_flow_config {
   int32_t dim;              /* d */
   int32_t depth;            /* number of SingleBlocks */
-  int32_t n_hidden_layers;  /* len(intmediate); this release builds 1 */
+  int32_t n_hidden_layers;  /* len(intmediate): 1 (streaming fast path, width <= 256) to 3 (generic path, widths <= 32) */
   int32_t hidden;           /* intmediate[0] */
   int32_t variant;          /* VMCPDE_NO_ADD ... */
   int32_t latent;           /* VMCPDE_GAUSS | VMCPDE_STUDENT_T */
   const int32_t* ind_up;    /* host, depth * (dim/2)       : var_state.py:116 */
   const int32_t* ind_down;  /* host, depth * (dim - dim/2) : var_state.py:117 */
   const double* offset;     /* host, dim : network_args["offset"] */
+  const int32_t* hidden_widths; /* host, n_hidden_layers entries = intmediate (net.py:53-58); may be NULL when
+                                   n_hidden_layers == 1 (then `hidden` is used) */
 } vmcpde_flow_config;
 
 /* evolutionEq.EvolutionEquation parameters, evolutionEq.py:61-77 */

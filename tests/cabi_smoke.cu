@@ -22,7 +22,7 @@ int main() {
   const int d = 2, depth = 4, N = 4096;
   int32_t up[depth] = {0, 1, 0, 1}, down[depth] = {1, 0, 1, 0};
   double offset[d] = {0.0, 0.0};
-  vmcpde_flow_config cfg{d, depth, 1, 1, VMCPDE_NO_ADD, VMCPDE_GAUSS, up, down, offset};
+  vmcpde_flow_config cfg{d, depth, 1, 1, VMCPDE_NO_ADD, VMCPDE_GAUSS, up, down, offset, nullptr};
   vmcpde_flow* flow = nullptr;
   CK(vmcpde_flow_create(&cfg, &flow));
   const int P = vmcpde_flow_num_params(flow), Pp = vmcpde_padded_params(P);

@@ -55,8 +55,14 @@ def test_host_only_entry_points(lib):
     bad, keep2 = _capi.make_flow_config(4, 1, (3,), "no_add", "Gauss", [[0, 0]], [[1, 2]], np.zeros(4))
     assert lib.vmcpde_flow_create(ctypes.byref(bad), ctypes.byref(h)) != 0
     assert b"partition" in lib.vmcpde_last_error()
-    two, keep3 = _capi.make_flow_config(4, 1, (3, 3), "no_add", "Gauss", [[0, 1]], [[2, 3]], np.zeros(4))
-    assert lib.vmcpde_flow_create(ctypes.byref(two), ctypes.byref(h)) == 2  # VMCPDE_EUNSUPPORTED: one hidden layer only
+    two, keep3 = _capi.make_flow_config(4, 1, (3, 5), "no_add", "Gauss", [[0, 1]], [[2, 3]], np.zeros(4))
+    _lib.check(lib.vmcpde_flow_create(ctypes.byref(two), ctypes.byref(h)))       # several hidden layers: net.py:53-58 loops over `intmediate`
+    assert lib.vmcpde_flow_num_params(h) == 6 + 4 + 4 + 2 * ((3 + 2 * 3) + (5 + 3 * 5) + (2 + 5 * 2))
+    lib.vmcpde_flow_destroy(h)
+    four, keep4 = _capi.make_flow_config(4, 1, (3, 3, 3, 3), "no_add", "Gauss", [[0, 1]], [[2, 3]], np.zeros(4))
+    assert lib.vmcpde_flow_create(ctypes.byref(four), ctypes.byref(h)) == 2  # VMCPDE_EUNSUPPORTED: at most three hidden layers
+    wide, keep5 = _capi.make_flow_config(4, 1, (3, 40), "no_add", "Gauss", [[0, 1]], [[2, 3]], np.zeros(4))
+    assert lib.vmcpde_flow_create(ctypes.byref(wide), ctypes.byref(h)) == 2  # ... of at most 32 units each on the generic path
 
 
 def test_string_sorted_block_order(lib):

@@ -40,7 +40,9 @@ CASES = [(2, 4, 1, "no_add", "Gauss", "diffusion", 1000),
          (3, 2, 3, "no_add", "Gauss", "diffusion", 50),
          (5, 2, 4, "different_add", "Gauss", "diffusion_drift", 50),
          (2, 12, 2, "no_add", "Gauss", "diffusion", 40),
-         (6, 0, 1, "no_add", "Gauss", "diffusion", 40)]
+         (6, 0, 1, "no_add", "Gauss", "diffusion", 40),
+         (6, 3, (4, 7), "different_add", "Gauss", "advection_hamiltonian_wDiss", 300),   # several hidden layers (net.py:53-58)
+         (4, 2, (3, 5, 2), "no_add", "Student_t", "diffusion", 200)]
 
 
 @pytest.mark.parametrize("d,depth,h,variant,latent,eqname,n", CASES)
@@ -49,10 +51,11 @@ def test_sampler_local_terms_moments_gram(L, d, depth, h, variant, latent, eqnam
     rng = np.random.default_rng(d * 1000 + depth * 10 + n)
     ups, downs, _ = flow.make_index_splits(d, depth, 1)
     off = rng.normal(size=d) * 0.3
-    spec = flow.FlowSpec(dim=d, depth=depth, hidden=(h,), latent=latent, variant=variant, offset=off, inds_up=ups, inds_down=downs)
+    hidden = h if isinstance(h, tuple) else (h,)
+    spec = flow.FlowSpec(dim=d, depth=depth, hidden=hidden, latent=latent, variant=variant, offset=off, inds_up=ups, inds_down=downs)
     th = flow.init_params(spec, 1) + 0.05 * rng.normal(size=spec.num_params)
     st = flow.OracleState(spec, th)
-    cfg, keep = _capi.make_flow_config(d, depth, (h,), variant, latent, ups, downs, off)
+    cfg, keep = _capi.make_flow_config(d, depth, hidden, variant, latent, ups, downs, off)
     fh = C.c_void_p()
     _lib.check(L.vmcpde_flow_create(C.byref(cfg), C.byref(fh)))
     P = L.vmcpde_flow_num_params(fh)

@@ -25,11 +25,12 @@ def build(d, depth, h, variant, latent, eqname, offset):
     smp = sampler.Sampler(dim=d, numChains=30, name=latent, mcmc_info={"offset": offset, "bound": 0.25})
     net.SingleBlock.different_add = (variant == "different_add")   # the reference selects variants by editing class defaults
     try:
-        vs = var_state.VarState(smp, d, 1, depth, network_args={"intmediate": (h,), "offset": offset, "latentSpaceName": latent, "dim": d})
+        vs = var_state.VarState(smp, d, 1, depth, network_args={"intmediate": h if isinstance(h, tuple) else (h,), "offset": offset,
+                                                               "latentSpaceName": latent, "dim": d})
     finally:
         net.SingleBlock.different_add = False
     eq = evolutionEq.EvolutionEquation(dim=d, name=eqname)
-    spec = oflow.FlowSpec(dim=d, depth=depth, hidden=(h,), latent=latent, variant=variant, offset=offset,
+    spec = oflow.FlowSpec(dim=d, depth=depth, hidden=h if isinstance(h, tuple) else (h,), latent=latent, variant=variant, offset=offset,
                           inds_up=vs.net.inds_up, inds_down=vs.net.inds_down)
     assert spec.num_params == vs.numParameters
     return smp, vs, eq, spec
@@ -40,7 +41,8 @@ RHS_CASES = [(2, 4, 1, "no_add", "Gauss", "diffusion", 10000, np.zeros(2)),     
              (8, 4, 4, "no_add", "Gauss", "diffusion", 5000, np.zeros(8)),                        # P = 364
              (4, 3, 6, "no_add", "Gauss", "diffusion_anisotropic", 3000, np.zeros(4)),
              (2, 4, 2, "no_add", "Gauss", "advection_hamiltonian", 2000, np.ones(2)),              # 'harmonicOsc'
-             (2, 4, 85, "no_add", "Gauss", "diffusion", 4096, np.zeros(2))]                       # BASELINE C2 architecture, P = 2053:
+             (2, 4, 85, "no_add", "Gauss", "diffusion", 4096, np.zeros(2)),
+             (4, 3, (6, 4), "no_add", "Gauss", "diffusion", 3000, np.zeros(4))]                 # intmediate of length 2 through the Python surface                       # BASELINE C2 architecture, P = 2053:
                                                                                                   # blocked eigensolver incl. the lower-triangle mode
 
 

@@ -19,6 +19,9 @@ def relerr(a, b):
 
 
 CASES = [(2, 4, 1, "no_add", "Gauss", "diffusion"),
+         (4, 3, (5, 3), "no_add", "Gauss", "diffusion"),                             # two hidden layers (net.py:53-58)
+         (6, 2, (4, 6, 3), "different_add", "Student_t", "advection_hamiltonian_wDiss"),   # three, all four trafos per block
+         (5, 2, (2, 7), "add_s", "Gauss", "diffusion_anisotropic"),
          (2, 4, 7, "no_add", "Gauss", "advection_paper"),
          (6, 3, 5, "different_add", "Gauss", "advection_hamiltonian_wDiss"),
          (6, 2, 4, "no_add", "Student_t", "diffusion_drift"),
@@ -35,15 +38,16 @@ def test_local_terms_and_sampling_match_autograd(hostsim, d, depth, h, variant, 
     n = 24
     ups, downs, _ = flow.make_index_splits(d, depth, 1)
     off = rng.normal(size=d) * 0.3
-    spec = flow.FlowSpec(dim=d, depth=depth, hidden=(h,), latent=latent, variant=variant, offset=off, inds_up=ups, inds_down=downs)
+    hidden = h if isinstance(h, tuple) else (h,)
+    spec = flow.FlowSpec(dim=d, depth=depth, hidden=hidden, latent=latent, variant=variant, offset=off, inds_up=ups, inds_down=downs)
     th = flow.init_params(spec, 1) + 0.05 * rng.normal(size=spec.num_params)
     sl, _ = spec.slices()
     for name, (a, b, shp) in sl.items():
-        if name.endswith("Dense_1/kernel"):
+        if name.endswith(f"Dense_{len(hidden)}/kernel"):
             th[a:b] = 0.03 * rng.normal(size=b - a)
     st = flow.OracleState(spec, th)
     x = rng.normal(size=(n, d)) * 1.5
-    cfg, keep = _capi.make_flow_config(d, depth, (h,), variant, latent, ups, downs, off)
+    cfg, keep = _capi.make_flow_config(d, depth, hidden, variant, latent, ups, downs, off)
     assert hostsim.hostsim_num_params(C.byref(cfg)) == spec.num_params
     A = np.ascontiguousarray(tdvp.random_D_factor(d)) if eqname == "diffusion_anisotropic" else None
     eq = _capi.make_equation(eqname, dict(tdvp.EQ_PARAMS.get(eqname, {})), 0.3, A.ctypes.data if A is not None else None)

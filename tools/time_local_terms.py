@@ -18,3 +18,10 @@ for _ in range(5): run()
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 5
 print(f"local_terms n={n} P={h.P}: {ms:.3f} ms  ({n * h.Pp * 8 / ms / 1e9:.2f} TB/s of O written; x2 for N=2^18)")
+
+def samp(): vs.sample_range(key, 0, n, n)
+samp(); torch.cuda.synchronize()
+e0.record()
+for _ in range(5): samp()
+e1.record(); torch.cuda.synchronize()
+print(f"sample+logp n={n}: {e0.elapsed_time(e1) / 5:.3f} ms")

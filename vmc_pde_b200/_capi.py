@@ -12,7 +12,7 @@ class FlowConfig(C.Structure):
     _fields_ = [("dim", C.c_int32), ("depth", C.c_int32), ("n_hidden_layers", C.c_int32),
                 ("hidden", C.c_int32), ("variant", C.c_int32), ("latent", C.c_int32),
                 ("ind_up", C.POINTER(C.c_int32)), ("ind_down", C.POINTER(C.c_int32)),
-                ("offset", C.POINTER(C.c_double))]
+                ("offset", C.POINTER(C.c_double)), ("hidden_widths", C.POINTER(C.c_int32))]
 
 
 class Equation(C.Structure):
@@ -29,12 +29,13 @@ def make_flow_config(dim, depth, hidden, variant, latent, inds_up, inds_down, of
     off = np.ascontiguousarray(np.asarray(offset, dtype=np.float64).reshape(-1))
     if off.size != dim:
         raise ValueError("offset must have `dim` entries")
+    hw = np.ascontiguousarray(np.asarray(hidden if hidden else (0,), dtype=np.int32))
     cfg = FlowConfig(dim, depth, len(hidden), hidden[0] if hidden else 0,
                      VARIANTS[variant] if isinstance(variant, str) else int(variant),
                      LATENTS[latent] if isinstance(latent, str) else int(latent),
                      up.ctypes.data_as(C.POINTER(C.c_int32)), down.ctypes.data_as(C.POINTER(C.c_int32)),
-                     off.ctypes.data_as(C.POINTER(C.c_double)))
-    return cfg, (up, down, off)
+                     off.ctypes.data_as(C.POINTER(C.c_double)), hw.ctypes.data_as(C.POINTER(C.c_int32)))
+    return cfg, (up, down, off, hw)
 
 
 def make_equation(name, params, t=0.0, tangents_ptr=None):

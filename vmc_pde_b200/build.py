@@ -28,8 +28,9 @@ def _units():
     for f in PLAIN:
         if os.path.exists(os.path.join(CSRC, f)):
             units.append((f, [], f.replace(".cu", ".o")))
-    for d in DIMS:
-        units.append(("flow_kernels_dim.cu", [f"-DVMC_DIM={d}"], f"flow_kernels_dim{d}.o"))
+    for d in DIMS:        # largest first: the d = 12 multi-layer unit is the longest compile
+        for ml in (1, 0):  # without / with the generic multi-layer SingleTrafo path (flow_core.cuh: VMC_ML)
+            units.append(("flow_kernels_dim.cu", [f"-DVMC_DIM={d}", f"-DVMC_ML={ml}"], f"flow_kernels_dim{d}_ml{ml}.o"))
     return units
 
 

@@ -15,16 +15,17 @@ int set_error(int code, const std::string& msg) {
   return code;
 }
 
-#define VMC_DECL(Dv)                                                                                                  \
-  extern template int launch_sample<Dv>(const FlowMeta&, const double*, uint32_t, uint32_t, long long, long long,     \
+#define VMC_DECL2(Dv, MLv)                                                                                                  \
+  extern template int launch_sample<Dv, MLv>(const FlowMeta&, const double*, uint32_t, uint32_t, long long, long long,     \
                                         long long, const double*, double*, double*, double*, cudaStream_t);          \
-  extern template int launch_logp<Dv>(const FlowMeta&, const double*, const double*, long long, double*, cudaStream_t); \
-  extern template int launch_local_terms<Dv>(const FlowMeta&, const double*, const double*, long long, const EqParams&, \
+  extern template int launch_logp<Dv, MLv>(const FlowMeta&, const double*, const double*, long long, double*, cudaStream_t); \
+  extern template int launch_local_terms<Dv, MLv>(const FlowMeta&, const double*, const double*, long long, const EqParams&, \
                                              const double*, double*, double*, double*, double*, double*, long long,   \
                                              cudaStream_t);                                                           \
-  extern template int launch_transform<Dv>(const FlowMeta&, const double*, const double*, long long, int, double*,    \
+  extern template int launch_transform<Dv, MLv>(const FlowMeta&, const double*, const double*, long long, int, double*,    \
                                            double*, double*, cudaStream_t);                                           \
-  extern template int launch_hessian<Dv>(const FlowMeta&, const double*, const double*, long long, double*, cudaStream_t);
+  extern template int launch_hessian<Dv, MLv>(const FlowMeta&, const double*, const double*, long long, double*, cudaStream_t);
+#define VMC_DECL(Dv) VMC_DECL2(Dv, 0) VMC_DECL2(Dv, 1)
 VMC_FOR_EACH_DIM(VMC_DECL)
 
 __global__ void normal_kernel(uint32_t k0, uint32_t k1, long long first, long long n, unsigned long long total,
@@ -77,7 +78,7 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_sample(const vmcpde
   const FlowMeta& m = f->meta;
   cudaStream_t s = (cudaStream_t)stream;
   switch (m.d) {
-#define X(Dv) VMC_CASE(Dv, (launch_sample<D>(m, theta, key0, key1, first, n, n_total, chi2, x, logp, z_out, s)))
+#define X(Dv) VMC_CASE(Dv, (m.nl > 1 ? launch_sample<D, 1>(m, theta, key0, key1, first, n, n_total, chi2, x, logp, z_out, s) : launch_sample<D, 0>(m, theta, key0, key1, first, n, n_total, chi2, x, logp, z_out, s)))
     VMC_FOR_EACH_DIM(X)
 #undef X
   }
@@ -107,7 +108,7 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_logp(const vmcpde_f
   const FlowMeta& m = f->meta;
   cudaStream_t s = (cudaStream_t)stream;
   switch (m.d) {
-#define X(Dv) VMC_CASE(Dv, (launch_logp<D>(m, theta, x, n, logp, s)))
+#define X(Dv) VMC_CASE(Dv, (m.nl > 1 ? launch_logp<D, 1>(m, theta, x, n, logp, s) : launch_logp<D, 0>(m, theta, x, n, logp, s)))
     VMC_FOR_EACH_DIM(X)
 #undef X
   }
@@ -126,7 +127,7 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_local_terms(const v
   EqParams e{eq->mode, eq->D, eq->mu, eq->m, eq->omega, eq->lam, eq->T, eq->gamma, eq->t};
   cudaStream_t s = (cudaStream_t)stream;
   switch (m.d) {
-#define X(Dv) VMC_CASE(Dv, (launch_local_terms<D>(m, theta, x, n, e, eq->tangents, eloc, logp, grad, lap, O, ldo, s)))
+#define X(Dv) VMC_CASE(Dv, (m.nl > 1 ? launch_local_terms<D, 1>(m, theta, x, n, e, eq->tangents, eloc, logp, grad, lap, O, ldo, s) : launch_local_terms<D, 0>(m, theta, x, n, e, eq->tangents, eloc, logp, grad, lap, O, ldo, s)))
     VMC_FOR_EACH_DIM(X)
 #undef X
   }
@@ -139,7 +140,7 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_hessian(const vmcpd
   const FlowMeta& m = f->meta;
   cudaStream_t s = (cudaStream_t)stream;
   switch (m.d) {
-#define X(Dv) VMC_CASE(Dv, (launch_hessian<D>(m, theta, x, n, H, s)))
+#define X(Dv) VMC_CASE(Dv, (m.nl > 1 ? launch_hessian<D, 1>(m, theta, x, n, H, s) : launch_hessian<D, 0>(m, theta, x, n, H, s)))
     VMC_FOR_EACH_DIM(X)
 #undef X
   }
@@ -153,7 +154,7 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_flow_transform(cons
   const FlowMeta& m = f->meta;
   cudaStream_t s = (cudaStream_t)stream;
   switch (m.d) {
-#define X(Dv) VMC_CASE(Dv, (launch_transform<D>(m, theta, x, n, inverse, y, logjac, latent_logpdf_of_input, s)))
+#define X(Dv) VMC_CASE(Dv, (m.nl > 1 ? launch_transform<D, 1>(m, theta, x, n, inverse, y, logjac, latent_logpdf_of_input, s) : launch_transform<D, 0>(m, theta, x, n, inverse, y, logjac, latent_logpdf_of_input, s)))
     VMC_FOR_EACH_DIM(X)
 #undef X
   }

@@ -15,8 +15,10 @@
 
 #ifdef __CUDACC__
 #define VMC_HD __host__ __device__ __forceinline__
+#define VMC_HD_COLD __host__ __device__ __noinline__   // rarely taken paths kept out of line: the one-layer fast path keeps its registers
 #else
 #define VMC_HD inline
+#define VMC_HD_COLD inline
 #endif
 
 namespace vmc {
@@ -34,8 +36,17 @@ enum Equation {                                                             // e
   kAdvectionHamiltonian = 3, kAdvectionPaper = 4, kAdvectionHamiltonianWDiss = 5
 };
 
+// VMC_ML: the per-dimension kernels are compiled twice, without (0) and with (1) the generic multi-layer SingleTrafo path, so the
+// one-hidden-layer kernels keep the registers and stack frame they had before the generic path existed.
+#ifndef VMC_ML
+#define VMC_ML 1
+#endif
+constexpr int kMaxLayers = 3;    // hidden layers per SingleTrafo (net.py:53-58 loops over `intmediate`)
+constexpr int kMLWidth = 32;     // widest hidden layer of the multi-layer path (its jets live in per-thread arrays)
+
 struct FlowMeta {
   int d, depth, h, variant, latent, P;
+  int nl, hw[kMaxLayers];          // hidden layers and their widths (hw[0] == h); nl == 1 is the streaming fast path
   int off_L, off_Ldiag, off_dist, off_mu;
   int block_off[kMaxDepth];        // start of "blocks_b" in the flat vector (string-sorted order)
   int8_t up[kMaxDepth][kMaxHalf];   // ind_up   (d/2 entries)
@@ -49,20 +60,68 @@ struct EqParams {  // evolutionEq.py:61-77
 };
 
 // ------------------------------------------------------------------------------------------------
-struct Trafo {  // one SingleTrafo with a single hidden layer: Dense_0{bias,kernel}, Dense_1{bias,kernel}
-  const double *b1, *W1, *b2, *W2;
+struct Trafo {  // one SingleTrafo: Dense_0{bias,kernel} ... Dense_nl{bias,kernel} (net.py:44-61)
+  const double *b1, *W1, *b2, *W2;   // the two layers of the single-hidden-layer fast path
   int h;
+  int nl, hw[kMaxLayers];            // nl > 1: generic path, layers walked from p0
+  const double* p0;
 };
 VMC_HD int trafo_size(int din, int dout, int h) { return h + din * h + dout + h * dout; }
 VMC_HD Trafo trafo_at(const double* th, int off, int din, int dout, int h) {
   Trafo t;
   t.b1 = th + off; t.W1 = t.b1 + h; t.b2 = t.W1 + din * h; t.W2 = t.b2 + dout; t.h = h;
+  t.nl = 1; t.hw[0] = h; t.p0 = th + off;
   return t;
+}
+VMC_HD int trafo_size(int din, int dout, const FlowMeta& m) {
+  if (!VMC_ML || m.nl == 1) return trafo_size(din, dout, m.h);
+  int s = 0, in = din;
+  for (int l = 0; l < m.nl; ++l) { s += m.hw[l] + in * m.hw[l]; in = m.hw[l]; }
+  return s + dout + in * dout;
+}
+VMC_HD Trafo trafo_at(const double* th, int off, int din, int dout, const FlowMeta& m) {
+  Trafo t = trafo_at(th, off, din, dout, m.h);
+#if VMC_ML
+  t.nl = m.nl;
+  for (int l = 0; l < kMaxLayers; ++l) t.hw[l] = l < m.nl ? m.hw[l] : 0;
+#endif
+  return t;
+}
+
+// ---- generic multi-layer path (nl > 1): layer l maps prev (nprev) -> hw[l] with tanh, the last layer -> NO with alpha*tanh.
+// Parameters of layer l: bias[hw[l]], kernel[nprev][hw[l]] (row-major, flax Dense).  `hid` receives the activations of all
+// hidden layers, one after the other (sum of widths <= kMaxHidden).
+template <int NI, int NO>
+VMC_HD_COLD void trafo_value_ml(const Trafo& t, const double* a0, double* out, double* hid) {
+  double buf[2][kMLWidth];
+  const double* prev = a0;
+  const double* p = t.p0;
+  int nprev = NI, hoff = 0;
+  for (int l = 0; l < t.nl; ++l) {
+    const int h = t.hw[l];
+    const double *b = p, *W = p + h;
+    double* cur = buf[l & 1];
+    for (int j = 0; j < h; ++j) {
+      double s = b[j];
+      for (int i = 0; i < nprev; ++i) s = fma(W[i * h + j], prev[i], s);
+      cur[j] = tanh(s);
+      if (hid) hid[hoff + j] = cur[j];
+    }
+    p += h + nprev * h; prev = cur; nprev = h; hoff += h;
+  }
+  const double *b = p, *W = p + NO;
+#pragma unroll
+  for (int o = 0; o < NO; ++o) {
+    double s = b[o];
+    for (int j = 0; j < nprev; ++j) s = fma(W[j * NO + o], prev[j], s);
+    out[o] = kAlpha * tanh(s);
+  }
 }
 
 // value-only forward; optionally keeps the hidden activations for the reverse sweep
 template <int NI, int NO>
 VMC_HD void trafo_value(const Trafo& t, const double* a0, double* out, double* hid) {
+  if (VMC_ML && t.nl > 1) { trafo_value_ml<NI, NO>(t, a0, out, hid); return; }
   double acc[NO];
 #pragma unroll
   for (int o = 0; o < NO; ++o) acc[o] = t.b2[o];
@@ -120,7 +179,36 @@ template <int D> VMC_HD void jet_mulexp(Jet<D>& u, const Jet<D>& s, const double
 }
 
 template <int D, int NI, int NO>
+VMC_HD_COLD void trafo_jet_ml(const Trafo& t, const Jet<D>* a0, const double* w, Jet<D>* out) {
+  Jet<D> buf[2][kMLWidth];
+  const Jet<D>* prev = a0;
+  const double* p = t.p0;
+  int nprev = NI;
+  for (int l = 0; l < t.nl; ++l) {
+    const int h = t.hw[l];
+    const double *b = p, *W = p + h;
+    Jet<D>* cur = buf[l & 1];
+    for (int j = 0; j < h; ++j) {
+      Jet<D> q;
+      jet_const(q, b[j]);
+      for (int i = 0; i < nprev; ++i) jet_axpy(q, W[i * h + j], prev[i]);
+      jet_tanh(q, w, 1.0, cur[j]);
+    }
+    p += h + nprev * h; prev = cur; nprev = h;
+  }
+  const double *b = p, *W = p + NO;
+#pragma unroll
+  for (int o = 0; o < NO; ++o) {
+    Jet<D> q;
+    jet_const(q, b[o]);
+    for (int j = 0; j < nprev; ++j) jet_axpy(q, W[j * NO + o], prev[j]);
+    jet_tanh(q, w, kAlpha, out[o]);
+  }
+}
+
+template <int D, int NI, int NO>
 VMC_HD void trafo_jet(const Trafo& t, const Jet<D>* a0, const double* w, Jet<D>* out) {
+  if (VMC_ML && t.nl > 1) { trafo_jet_ml<D, NI, NO>(t, a0, w, out); return; }
   Jet<D> acc[NO];
 #pragma unroll
   for (int o = 0; o < NO; ++o) jet_const(acc[o], t.b2[o]);
@@ -141,9 +229,78 @@ VMC_HD void trafo_jet(const Trafo& t, const Jet<D>* a0, const double* w, Jet<D>*
 // Reverse sweep through one trafo.  dout = d logp / d(trafo output).  Emits the parameter gradients in
 // flat order (Dense_0/bias, Dense_0/kernel, Dense_1/bias, Dense_1/kernel) when EMIT, and accumulates
 // d logp / d(input) into din_acc when INGRAD.  `hid` holds the hidden activations from trafo_value.
+// generic multi-layer reverse: the deltas of all hidden layers go to dh (same offsets as hid), then the gradients are
+// emitted layer by layer in flat order
+template <int NI, int NO, bool EMIT, bool INGRAD, class Emit>
+VMC_HD_COLD void trafo_reverse_ml(const Trafo& t, const double* a0, const double* out, const double* dout,
+                             const double* hid, double* dh, double* din_acc, Emit& em) {
+  double dp2[NO];
+#pragma unroll
+  for (int o = 0; o < NO; ++o) {
+    const double y = out[o] * (1.0 / kAlpha);
+    dp2[o] = dout[o] * kAlpha * (1.0 - y * y);
+  }
+  // parameter / activation offsets of the layers
+  int poff[kMaxLayers + 1], hoff[kMaxLayers + 1], nin[kMaxLayers + 1];
+  {
+    int po = 0, ho = 0, in = NI;
+    for (int l = 0; l < t.nl; ++l) { poff[l] = po; hoff[l] = ho; nin[l] = in; po += t.hw[l] + in * t.hw[l]; ho += t.hw[l]; in = t.hw[l]; }
+    poff[t.nl] = po; hoff[t.nl] = ho; nin[t.nl] = in;
+  }
+  {  // last hidden layer from the output layer
+    const int L = t.nl - 1, h = t.hw[L];
+    const double* W = t.p0 + poff[t.nl] + NO;
+    for (int j = 0; j < h; ++j) {
+      double s = 0.0;
+#pragma unroll
+      for (int o = 0; o < NO; ++o) s = fma(W[j * NO + o], dp2[o], s);
+      const double a = hid[hoff[L] + j];
+      dh[hoff[L] + j] = (1.0 - a * a) * s;
+    }
+  }
+  for (int l = t.nl - 2; l >= 0; --l) {  // earlier hidden layers
+    const int h = t.hw[l], hn = t.hw[l + 1];
+    const double* W = t.p0 + poff[l + 1] + hn;     // kernel of layer l + 1: [h][hn]
+    for (int i = 0; i < h; ++i) {
+      double s = 0.0;
+      for (int j = 0; j < hn; ++j) s = fma(W[i * hn + j], dh[hoff[l + 1] + j], s);
+      const double a = hid[hoff[l] + i];
+      dh[hoff[l] + i] = (1.0 - a * a) * s;
+    }
+  }
+  if (EMIT) {
+    for (int l = 0; l < t.nl; ++l) {
+      const int h = t.hw[l];
+      for (int j = 0; j < h; ++j) em.put(dh[hoff[l] + j]);                         // Dense_l/bias
+      for (int i = 0; i < nin[l]; ++i) {                                           // Dense_l/kernel [nin][h]
+        const double ai = l == 0 ? a0[i] : hid[hoff[l - 1] + i];
+        for (int j = 0; j < h; ++j) em.put(ai * dh[hoff[l] + j]);
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < NO; ++o) em.put(dp2[o]);                                   // Dense_nl/bias
+    const int L = t.nl - 1;
+    for (int j = 0; j < t.hw[L]; ++j) {
+#pragma unroll
+      for (int o = 0; o < NO; ++o) em.put(hid[hoff[L] + j] * dp2[o]);              // Dense_nl/kernel [h][NO]
+    }
+  }
+  if (INGRAD) {
+    const int h = t.hw[0];
+    const double* W = t.p0 + h;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      double s = 0.0;
+      for (int j = 0; j < h; ++j) s = fma(W[i * h + j], dh[j], s);
+      din_acc[i] += s;
+    }
+  }
+}
+
 template <int NI, int NO, bool EMIT, bool INGRAD, class Emit>
 VMC_HD void trafo_reverse(const Trafo& t, const double* a0, const double* out, const double* dout,
                           const double* hid, double* dh, double* din_acc, Emit& em) {
+  if (VMC_ML && t.nl > 1) { trafo_reverse_ml<NI, NO, EMIT, INGRAD>(t, a0, out, dout, hid, dh, din_acc, em); return; }
   double dp2[NO];
 #pragma unroll
   for (int o = 0; o < NO; ++o) {
@@ -231,14 +388,14 @@ VMC_HD double latent_logpdf(const FlowMeta& m, const double* th, const double* y
 template <int D>
 VMC_HD double block_forward_value(const FlowMeta& m, const double* th, int b, double* z) {
   constexpr int D1 = D / 2, D2 = D - D / 2;
-  const int T1 = trafo_size(D1, D2, m.h), T2 = trafo_size(D2, D1, m.h);
+  const int T1 = trafo_size(D1, D2, m), T2 = trafo_size(D2, D1, m);
   const int o = m.block_off[b];
   double u1[D1], u2[D2], s2[D1], s1[D2], lj = 0.0;
 #pragma unroll
   for (int i = 0; i < D1; ++i) u1[i] = z[m.up[b][i]];
 #pragma unroll
   for (int i = 0; i < D2; ++i) u2[i] = z[m.down[b][i]];
-  trafo_value<D2, D1>(trafo_at(th, o + T1, D2, D1, m.h), u2, s2, nullptr);
+  trafo_value<D2, D1>(trafo_at(th, o + T1, D2, D1, m), u2, s2, nullptr);
   if (m.variant == kJacEq1) {
 #pragma unroll
     for (int i = 0; i < D1; ++i) u1[i] += s2[i];
@@ -250,12 +407,12 @@ VMC_HD double block_forward_value(const FlowMeta& m, const double* th, int b, do
       for (int i = 0; i < D1; ++i) u1[i] += s2[i];
     } else if (m.variant == kDifferentAdd) {
       double t2[D1];
-      trafo_value<D2, D1>(trafo_at(th, o + 2 * T1 + T2, D2, D1, m.h), u2, t2, nullptr);
+      trafo_value<D2, D1>(trafo_at(th, o + 2 * T1 + T2, D2, D1, m), u2, t2, nullptr);
 #pragma unroll
       for (int i = 0; i < D1; ++i) u1[i] += t2[i];
     }
   }
-  trafo_value<D1, D2>(trafo_at(th, o, D1, D2, m.h), u1, s1, nullptr);
+  trafo_value<D1, D2>(trafo_at(th, o, D1, D2, m), u1, s1, nullptr);
   if (m.variant == kJacEq1) {
 #pragma unroll
     for (int i = 0; i < D2; ++i) u2[i] += s1[i];
@@ -267,7 +424,7 @@ VMC_HD double block_forward_value(const FlowMeta& m, const double* th, int b, do
       for (int i = 0; i < D2; ++i) u2[i] += s1[i];
     } else if (m.variant == kDifferentAdd) {
       double t1[D2];
-      trafo_value<D1, D2>(trafo_at(th, o + T1 + T2, D1, D2, m.h), u1, t1, nullptr);
+      trafo_value<D1, D2>(trafo_at(th, o + T1 + T2, D1, D2, m), u1, t1, nullptr);
 #pragma unroll
       for (int i = 0; i < D2; ++i) u2[i] += t1[i];
     }
@@ -283,14 +440,14 @@ VMC_HD double block_forward_value(const FlowMeta& m, const double* th, int b, do
 template <int D>
 VMC_HD double block_inverse_value(const FlowMeta& m, const double* th, int b, double* z) {
   constexpr int D1 = D / 2, D2 = D - D / 2;
-  const int T1 = trafo_size(D1, D2, m.h), T2 = trafo_size(D2, D1, m.h);
+  const int T1 = trafo_size(D1, D2, m), T2 = trafo_size(D2, D1, m);
   const int o = m.block_off[b];
   double v1[D1], v2[D2], s1[D2], s2[D1], lj = 0.0;
 #pragma unroll
   for (int i = 0; i < D1; ++i) v1[i] = z[m.up[b][i]];
 #pragma unroll
   for (int i = 0; i < D2; ++i) v2[i] = z[m.down[b][i]];
-  trafo_value<D1, D2>(trafo_at(th, o, D1, D2, m.h), v1, s1, nullptr);
+  trafo_value<D1, D2>(trafo_at(th, o, D1, D2, m), v1, s1, nullptr);
   if (m.variant == kJacEq1) {
 #pragma unroll
     for (int i = 0; i < D2; ++i) v2[i] -= s1[i];
@@ -300,14 +457,14 @@ VMC_HD double block_inverse_value(const FlowMeta& m, const double* th, int b, do
       for (int i = 0; i < D2; ++i) v2[i] -= s1[i];
     } else if (m.variant == kDifferentAdd) {
       double t1[D2];
-      trafo_value<D1, D2>(trafo_at(th, o + T1 + T2, D1, D2, m.h), v1, t1, nullptr);
+      trafo_value<D1, D2>(trafo_at(th, o + T1 + T2, D1, D2, m), v1, t1, nullptr);
 #pragma unroll
       for (int i = 0; i < D2; ++i) v2[i] -= t1[i];
     }
 #pragma unroll
     for (int i = 0; i < D2; ++i) { v2[i] *= exp(-s1[i]); lj -= s1[i]; }
   }
-  trafo_value<D2, D1>(trafo_at(th, o + T1, D2, D1, m.h), v2, s2, nullptr);
+  trafo_value<D2, D1>(trafo_at(th, o + T1, D2, D1, m), v2, s2, nullptr);
   if (m.variant == kJacEq1) {
 #pragma unroll
     for (int i = 0; i < D1; ++i) v1[i] -= s2[i];
@@ -317,7 +474,7 @@ VMC_HD double block_inverse_value(const FlowMeta& m, const double* th, int b, do
       for (int i = 0; i < D1; ++i) v1[i] -= s2[i];
     } else if (m.variant == kDifferentAdd) {
       double t2[D1];
-      trafo_value<D2, D1>(trafo_at(th, o + 2 * T1 + T2, D2, D1, m.h), v2, t2, nullptr);
+      trafo_value<D2, D1>(trafo_at(th, o + 2 * T1 + T2, D2, D1, m), v2, t2, nullptr);
 #pragma unroll
       for (int i = 0; i < D1; ++i) v1[i] -= t2[i];
     }
@@ -360,7 +517,7 @@ VMC_HD double sample_from_latent(const FlowMeta& m, const double* th, const doub
 template <int D, int NT>
 VMC_HD void block_forward_jet(const FlowMeta& m, const double* th, int b, const double* w, Jet<NT>* z, Jet<NT>& lj) {
   constexpr int D1 = D / 2, D2 = D - D / 2;
-  const int T1 = trafo_size(D1, D2, m.h), T2 = trafo_size(D2, D1, m.h);
+  const int T1 = trafo_size(D1, D2, m), T2 = trafo_size(D2, D1, m);
   const int o = m.block_off[b];
   Jet<NT> u1[D1], u2[D2];
 #pragma unroll
@@ -369,7 +526,7 @@ VMC_HD void block_forward_jet(const FlowMeta& m, const double* th, int b, const 
   for (int i = 0; i < D2; ++i) u2[i] = z[m.down[b][i]];
   {
     Jet<NT> s2[D1];
-    trafo_jet<NT, D2, D1>(trafo_at(th, o + T1, D2, D1, m.h), u2, w, s2);
+    trafo_jet<NT, D2, D1>(trafo_at(th, o + T1, D2, D1, m), u2, w, s2);
     if (m.variant == kJacEq1) {
 #pragma unroll
       for (int i = 0; i < D1; ++i) jet_add(u1[i], s2[i]);
@@ -380,7 +537,7 @@ VMC_HD void block_forward_jet(const FlowMeta& m, const double* th, int b, const 
 #pragma unroll
         for (int i = 0; i < D1; ++i) jet_add(u1[i], s2[i]);
       } else if (m.variant == kDifferentAdd) {
-        trafo_jet<NT, D2, D1>(trafo_at(th, o + 2 * T1 + T2, D2, D1, m.h), u2, w, s2);
+        trafo_jet<NT, D2, D1>(trafo_at(th, o + 2 * T1 + T2, D2, D1, m), u2, w, s2);
 #pragma unroll
         for (int i = 0; i < D1; ++i) jet_add(u1[i], s2[i]);
       }
@@ -388,7 +545,7 @@ VMC_HD void block_forward_jet(const FlowMeta& m, const double* th, int b, const 
   }
   {
     Jet<NT> s1[D2];
-    trafo_jet<NT, D1, D2>(trafo_at(th, o, D1, D2, m.h), u1, w, s1);
+    trafo_jet<NT, D1, D2>(trafo_at(th, o, D1, D2, m), u1, w, s1);
     if (m.variant == kJacEq1) {
 #pragma unroll
       for (int i = 0; i < D2; ++i) jet_add(u2[i], s1[i]);
@@ -399,7 +556,7 @@ VMC_HD void block_forward_jet(const FlowMeta& m, const double* th, int b, const 
 #pragma unroll
         for (int i = 0; i < D2; ++i) jet_add(u2[i], s1[i]);
       } else if (m.variant == kDifferentAdd) {
-        trafo_jet<NT, D1, D2>(trafo_at(th, o + T1 + T2, D1, D2, m.h), u1, w, s1);
+        trafo_jet<NT, D1, D2>(trafo_at(th, o + T1 + T2, D1, D2, m), u1, w, s1);
 #pragma unroll
         for (int i = 0; i < D2; ++i) jet_add(u2[i], s1[i]);
       }
@@ -525,12 +682,12 @@ VMC_HD void logp_reverse(const FlowMeta& m, const double* th, const double* zfin
 #pragma unroll
   for (int a = 0; a < D; ++a) { z[a] = zfin[a]; dz[a] = 2.0 * f1 * r[a]; }
 
-  const int T1 = trafo_size(D1, D2, m.h), T2 = trafo_size(D2, D1, m.h);
+  const int T1 = trafo_size(D1, D2, m), T2 = trafo_size(D2, D1, m);
   double hid[kMaxHidden], dh[kMaxHidden];
   for (int b = m.depth - 1; b >= 0; --b) {
     const int o = m.block_off[b];
-    const Trafo ts1 = trafo_at(th, o, D1, D2, m.h), ts2 = trafo_at(th, o + T1, D2, D1, m.h);
-    const Trafo tt1 = trafo_at(th, o + T1 + T2, D1, D2, m.h), tt2 = trafo_at(th, o + 2 * T1 + T2, D2, D1, m.h);
+    const Trafo ts1 = trafo_at(th, o, D1, D2, m), ts2 = trafo_at(th, o + T1, D2, D1, m);
+    const Trafo tt1 = trafo_at(th, o + T1 + T2, D1, D2, m), tt2 = trafo_at(th, o + 2 * T1 + T2, D2, D1, m);
     double v1[D1], v2[D2], dv1[D1], dv2[D2];
 #pragma unroll
     for (int i = 0; i < D1; ++i) { v1[i] = z[m.up[b][i]]; dv1[i] = dz[m.up[b][i]]; }

@@ -57,7 +57,7 @@ struct WarpEmit {
   __device__ __forceinline__ void finish() { flush_window(); lo = cnt; }
 };
 
-template <int D>
+template <int D, int ML>
 __global__ void __launch_bounds__(kThreads)
 sample_kernel(const __grid_constant__ FlowMeta m, const double* __restrict__ theta, uint32_t k0, uint32_t k1,
               long long first, long long n, long long n_total, const double* __restrict__ chi2,
@@ -109,7 +109,7 @@ sample_kernel(const __grid_constant__ FlowMeta m, const double* __restrict__ the
   logp[i] = lp;
 }
 
-template <int D>
+template <int D, int ML>
 __global__ void __launch_bounds__(kThreads)
 logp_kernel(const __grid_constant__ FlowMeta m, const double* __restrict__ theta, const double* __restrict__ x,
             long long n, double* __restrict__ logp, int use_smem) {
@@ -123,7 +123,7 @@ logp_kernel(const __grid_constant__ FlowMeta m, const double* __restrict__ theta
   logp[i] = logp_value<D>(m, th, xi);
 }
 
-template <int D>
+template <int D, int ML>
 __global__ void __launch_bounds__(kThreads, VMC_LT_MINBLOCKS)
 local_terms_kernel(const __grid_constant__ FlowMeta m, const __grid_constant__ EqParams e,
                    const double* __restrict__ theta, const double* __restrict__ x, long long n,
@@ -171,7 +171,7 @@ local_terms_kernel(const __grid_constant__ FlowMeta m, const __grid_constant__ E
   }
 }
 
-template <int D>
+template <int D, int ML>
 __global__ void __launch_bounds__(kThreads)
 hessian_kernel(const __grid_constant__ FlowMeta m, const double* __restrict__ theta, const double* __restrict__ x,
                long long n, double* __restrict__ H, int use_smem) {
@@ -187,7 +187,7 @@ hessian_kernel(const __grid_constant__ FlowMeta m, const double* __restrict__ th
 }
 
 // INN map alone (net.py:168-182): y = INN(x) or INN^-1(x), its log-Jacobian, and log p_lat(x - offset)
-template <int D>
+template <int D, int ML>
 __global__ void __launch_bounds__(kThreads)
 transform_kernel(const __grid_constant__ FlowMeta m, const double* __restrict__ theta, const double* __restrict__ x,
                  long long n, int inv, double* __restrict__ y, double* __restrict__ logjac, double* __restrict__ lat_in,
@@ -208,6 +208,9 @@ transform_kernel(const __grid_constant__ FlowMeta m, const double* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+#ifndef VMC_ML
+#error "compile with -DVMC_DIM=<d> -DVMC_ML=<0|1>"
+#endif
 template <class K>
 static int prep_smem(K kernel, size_t bytes) {
   if (bytes > 48 * 1024) VMC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -215,30 +218,30 @@ static int prep_smem(K kernel, size_t bytes) {
 }
 static inline unsigned grid_for(long long n) { return (unsigned)((n + kThreads - 1) / kThreads); }
 
-template <int D>
+template <int D, int ML>
 int launch_sample(const FlowMeta& m, const double* theta, uint32_t k0, uint32_t k1, long long first, long long n,
                   long long n_total, const double* chi2, double* x, double* logp, double* zout, cudaStream_t s) {
   if (n <= 0) return 0;
   const size_t tb = (size_t)m.P * 8;
   const int use = tb <= kMaxThetaSmem;
   const size_t smem = use ? tb : 0;
-  if (int rc = prep_smem(sample_kernel<D>, smem)) return rc;
-  sample_kernel<D><<<grid_for(n), kThreads, smem, s>>>(m, theta, k0, k1, first, n, n_total, chi2, x, logp, zout, use);
+  if (int rc = prep_smem(sample_kernel<D, ML>, smem)) return rc;
+  sample_kernel<D, ML><<<grid_for(n), kThreads, smem, s>>>(m, theta, k0, k1, first, n, n_total, chi2, x, logp, zout, use);
   VMC_LAUNCH_CHECK("sample_kernel");
   return 0;
 }
-template <int D>
+template <int D, int ML>
 int launch_logp(const FlowMeta& m, const double* theta, const double* x, long long n, double* logp, cudaStream_t s) {
   if (n <= 0) return 0;
   const size_t tb = (size_t)m.P * 8;
   const int use = tb <= kMaxThetaSmem;
   const size_t smem = use ? tb : 0;
-  if (int rc = prep_smem(logp_kernel<D>, smem)) return rc;
-  logp_kernel<D><<<grid_for(n), kThreads, smem, s>>>(m, theta, x, n, logp, use);
+  if (int rc = prep_smem(logp_kernel<D, ML>, smem)) return rc;
+  logp_kernel<D, ML><<<grid_for(n), kThreads, smem, s>>>(m, theta, x, n, logp, use);
   VMC_LAUNCH_CHECK("logp_kernel");
   return 0;
 }
-template <int D>
+template <int D, int ML>
 int launch_local_terms(const FlowMeta& m, const double* theta, const double* x, long long n, const EqParams& e,
                        const double* tang, double* eloc, double* logp, double* grad, double* lap, double* O,
                        long long ldo, cudaStream_t s) {
@@ -250,45 +253,45 @@ int launch_local_terms(const FlowMeta& m, const double* theta, const double* x, 
   const int use = theta_smem_env >= 0 ? (theta_smem_env && tb <= kMaxThetaSmem) : (tb <= 24 * 1024);
   const int theta_doubles = use ? m.P : 0;
   const size_t smem = (size_t)theta_doubles * 8 + (O ? (kThreads / 32) * kStagePerWarp * 8 : 0);
-  if (int rc = prep_smem(local_terms_kernel<D>, smem)) return rc;
-  local_terms_kernel<D><<<grid_for(n), kThreads, smem, s>>>(m, e, theta, x, n, tang, eloc, logp, grad, lap, O, ldo,
+  if (int rc = prep_smem(local_terms_kernel<D, ML>, smem)) return rc;
+  local_terms_kernel<D, ML><<<grid_for(n), kThreads, smem, s>>>(m, e, theta, x, n, tang, eloc, logp, grad, lap, O, ldo,
                                                            use, theta_doubles);
   VMC_LAUNCH_CHECK("local_terms_kernel");
   return 0;
 }
-template <int D>
+template <int D, int ML>
 int launch_hessian(const FlowMeta& m, const double* theta, const double* x, long long n, double* H, cudaStream_t s) {
   if (n <= 0) return 0;
   const size_t tb = (size_t)m.P * 8;
   const int use = tb <= kMaxThetaSmem;
   const size_t smem = use ? tb : 0;
-  if (int rc = prep_smem(hessian_kernel<D>, smem)) return rc;
-  hessian_kernel<D><<<grid_for(n), kThreads, smem, s>>>(m, theta, x, n, H, use);
+  if (int rc = prep_smem(hessian_kernel<D, ML>, smem)) return rc;
+  hessian_kernel<D, ML><<<grid_for(n), kThreads, smem, s>>>(m, theta, x, n, H, use);
   VMC_LAUNCH_CHECK("hessian_kernel");
   return 0;
 }
 
-template <int D>
+template <int D, int ML>
 int launch_transform(const FlowMeta& m, const double* theta, const double* x, long long n, int inv, double* y,
                      double* logjac, double* lat_in, cudaStream_t s) {
   if (n <= 0) return 0;
   const size_t tb = (size_t)m.P * 8;
   const int use = tb <= kMaxThetaSmem;
   const size_t smem = use ? tb : 0;
-  if (int rc = prep_smem(transform_kernel<D>, smem)) return rc;
-  transform_kernel<D><<<grid_for(n), kThreads, smem, s>>>(m, theta, x, n, inv, y, logjac, lat_in, use);
+  if (int rc = prep_smem(transform_kernel<D, ML>, smem)) return rc;
+  transform_kernel<D, ML><<<grid_for(n), kThreads, smem, s>>>(m, theta, x, n, inv, y, logjac, lat_in, use);
   VMC_LAUNCH_CHECK("transform_kernel");
   return 0;
 }
-template int launch_transform<VMC_DIM>(const FlowMeta&, const double*, const double*, long long, int, double*, double*,
+template int launch_transform<VMC_DIM, VMC_ML>(const FlowMeta&, const double*, const double*, long long, int, double*, double*,
                                        double*, cudaStream_t);
 
-template int launch_sample<VMC_DIM>(const FlowMeta&, const double*, uint32_t, uint32_t, long long, long long, long long,
+template int launch_sample<VMC_DIM, VMC_ML>(const FlowMeta&, const double*, uint32_t, uint32_t, long long, long long, long long,
                                     const double*, double*, double*, double*, cudaStream_t);
-template int launch_logp<VMC_DIM>(const FlowMeta&, const double*, const double*, long long, double*, cudaStream_t);
-template int launch_local_terms<VMC_DIM>(const FlowMeta&, const double*, const double*, long long, const EqParams&,
+template int launch_logp<VMC_DIM, VMC_ML>(const FlowMeta&, const double*, const double*, long long, double*, cudaStream_t);
+template int launch_local_terms<VMC_DIM, VMC_ML>(const FlowMeta&, const double*, const double*, long long, const EqParams&,
                                          const double*, double*, double*, double*, double*, double*, long long,
                                          cudaStream_t);
-template int launch_hessian<VMC_DIM>(const FlowMeta&, const double*, const double*, long long, double*, cudaStream_t);
+template int launch_hessian<VMC_DIM, VMC_ML>(const FlowMeta&, const double*, const double*, long long, double*, cudaStream_t);
 
 }  // namespace vmc

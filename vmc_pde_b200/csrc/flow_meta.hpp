@@ -14,22 +14,37 @@ inline int make_flow_meta(const vmcpde_flow_config* c, FlowMeta* m, std::string*
   if (!c || !m) return fail(VMCPDE_EINVAL, "null config");
   if (c->dim < 2 || c->dim > kMaxDim) return fail(VMCPDE_EUNSUPPORTED, "dim must be in [2,16]");
   if (c->depth < 0 || c->depth > kMaxDepth) return fail(VMCPDE_EUNSUPPORTED, "depth must be in [0,32]");
-  if (c->depth > 0 && c->n_hidden_layers != 1)
-    return fail(VMCPDE_EUNSUPPORTED, "this build supports exactly one hidden layer per SingleTrafo");
-  if (c->depth > 0 && (c->hidden < 1 || c->hidden > kMaxHidden))
+  if (c->depth > 0 && (c->n_hidden_layers < 1 || c->n_hidden_layers > kMaxLayers))
+    return fail(VMCPDE_EUNSUPPORTED, "a SingleTrafo has 1 to 3 hidden layers in this build");
+  if (c->depth > 0 && c->n_hidden_layers > 1 && !c->hidden_widths)
+    return fail(VMCPDE_EINVAL, "hidden_widths is required when n_hidden_layers > 1");
+  int widths[kMaxLayers] = {c->hidden, 0, 0};
+  if (c->depth > 0 && c->hidden_widths)
+    for (int l = 0; l < c->n_hidden_layers; ++l) widths[l] = c->hidden_widths[l];
+  if (c->depth > 0 && c->n_hidden_layers == 1 && (widths[0] < 1 || widths[0] > kMaxHidden))
     return fail(VMCPDE_EUNSUPPORTED, "hidden width must be in [1,256]");
+  if (c->depth > 0 && c->n_hidden_layers > 1) {   // generic path: per-layer activations (and their jets) live in thread-local arrays
+    int sum = 0;
+    for (int l = 0; l < c->n_hidden_layers; ++l) {
+      if (widths[l] < 1 || widths[l] > kMLWidth) return fail(VMCPDE_EUNSUPPORTED, "with several hidden layers every width must be in [1,32]");
+      sum += widths[l];
+    }
+    if (sum > kMaxHidden) return fail(VMCPDE_EUNSUPPORTED, "sum of hidden widths must be <= 256");
+  }
   if (c->variant < 0 || c->variant > 3) return fail(VMCPDE_EINVAL, "bad coupling variant");
   if (c->latent < 0 || c->latent > 1) return fail(VMCPDE_EINVAL, "bad latent distribution");
   if (c->depth > 0 && c->dim < 2) return fail(VMCPDE_EINVAL, "coupling blocks need dim >= 2");
   const int d = c->dim, d1 = d / 2, d2 = d - d / 2;
   *m = FlowMeta{};
-  m->d = d; m->depth = c->depth; m->h = c->depth > 0 ? c->hidden : 1; m->variant = c->variant; m->latent = c->latent;
+  m->d = d; m->depth = c->depth; m->h = c->depth > 0 ? widths[0] : 1; m->variant = c->variant; m->latent = c->latent;
+  m->nl = c->depth > 0 ? c->n_hidden_layers : 1;
+  for (int l = 0; l < kMaxLayers; ++l) m->hw[l] = (c->depth > 0 && l < m->nl) ? widths[l] : (l == 0 ? 1 : 0);
   int off = 0;
   m->off_L = off; off += d * (d - 1) / 2;
   m->off_Ldiag = off; off += d;
   m->off_dist = off; off += (c->latent == VMCPDE_STUDENT_T) ? 1 : 0;
   m->off_mu = off; off += d;
-  const int T1 = trafo_size(d1, d2, m->h), T2 = trafo_size(d2, d1, m->h);
+  const int T1 = trafo_size(d1, d2, *m), T2 = trafo_size(d2, d1, *m);
   const int per_block = (c->variant == VMCPDE_DIFFERENT_ADD ? 2 : 1) * (T1 + T2);
   std::vector<int> order(c->depth);
   for (int b = 0; b < c->depth; ++b) order[b] = b;

@@ -39,7 +39,7 @@ vmcpde_flow* get_flow(int32_t dim, int32_t depth, int32_t hidden, int32_t varian
   std::lock_guard<std::mutex> lock(g_mu);
   auto it = g_flows.find(k);
   if (it != g_flows.end()) return it->second;
-  vmcpde_flow_config cfg{dim, depth, 1, hidden, variant, latent, ind_up.begin(), ind_down.begin(), offset.begin()};
+  vmcpde_flow_config cfg{dim, depth, 1, hidden, variant, latent, ind_up.begin(), ind_down.begin(), offset.begin(), nullptr};
   vmcpde_flow* f = nullptr;
   if (vmcpde_flow_create(&cfg, &f) != 0) return nullptr;
   g_flows[k] = f;
