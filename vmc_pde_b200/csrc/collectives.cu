@@ -12,6 +12,7 @@
 #include <dlfcn.h>
 #include <cstdint>
 #include <cstring>
+#include <string>
 #include "common.cuh"
 
 namespace vmc {
@@ -47,23 +48,34 @@ struct NcclApi {
 };
 
 static int nccl_api(NcclApi** out) {
-  static NcclApi api;
-  if (!api.handle) {
+  // resolved once (thread-safe static initialisation); a failed resolution is remembered and reported on every call
+  struct Resolved { NcclApi api; int rc = 0; std::string err; };
+  static const Resolved r = [] {
+    Resolved q;
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
     for (const char* nm : names) {
-      api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
-      if (api.handle) break;
+      q.api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (q.api.handle) break;
     }
-    if (!api.handle) return set_error(VMCPDE_EUNSUPPORTED, std::string("NCCL is not loadable (dlopen libnccl.so.2): ") + dlerror());
-    api.all_reduce = (NcclAllReduceFn)dlsym(api.handle, "ncclAllReduce");
-    api.get_unique_id = (NcclGetUniqueIdFn)dlsym(api.handle, "ncclGetUniqueId");
-    api.comm_init_rank = (int (*)(void**, int, NcclId, int))dlsym(api.handle, "ncclCommInitRank");
-    api.comm_destroy = (NcclCommDestroyFn)dlsym(api.handle, "ncclCommDestroy");
-    api.error_string = (NcclGetErrorStringFn)dlsym(api.handle, "ncclGetErrorString");
-    if (!api.all_reduce || !api.get_unique_id || !api.comm_init_rank || !api.comm_destroy)
-      return set_error(VMCPDE_EUNSUPPORTED, "libnccl.so.2 lacks ncclAllReduce / ncclGetUniqueId / ncclCommInitRank / ncclCommDestroy");
-  }
-  *out = &api;
+    if (!q.api.handle) {
+      const char* why = dlerror();
+      q.rc = VMCPDE_EUNSUPPORTED;
+      q.err = std::string("NCCL is not loadable (dlopen libnccl.so.2): ") + (why ? why : "unknown error");
+      return q;
+    }
+    q.api.all_reduce = (NcclAllReduceFn)dlsym(q.api.handle, "ncclAllReduce");
+    q.api.get_unique_id = (NcclGetUniqueIdFn)dlsym(q.api.handle, "ncclGetUniqueId");
+    q.api.comm_init_rank = (int (*)(void**, int, NcclId, int))dlsym(q.api.handle, "ncclCommInitRank");
+    q.api.comm_destroy = (NcclCommDestroyFn)dlsym(q.api.handle, "ncclCommDestroy");
+    q.api.error_string = (NcclGetErrorStringFn)dlsym(q.api.handle, "ncclGetErrorString");
+    if (!q.api.all_reduce || !q.api.get_unique_id || !q.api.comm_init_rank || !q.api.comm_destroy) {
+      q.rc = VMCPDE_EUNSUPPORTED;
+      q.err = "libnccl.so.2 lacks ncclAllReduce / ncclGetUniqueId / ncclCommInitRank / ncclCommDestroy";
+    }
+    return q;
+  }();
+  if (r.rc) return set_error(r.rc, r.err);
+  *out = const_cast<NcclApi*>(&r.api);
   return 0;
 }
 

@@ -366,8 +366,9 @@ class TDVP:
     def sample_partition(self, N, R, P, pipelined=None):
         """[(first, n)] per rank.  Equal contiguous shards unless the solve is pipelined: then the solver rank,
         which spends E(P) seconds in the serial stages of the eigensolver while the others build the SExp / C_EO Grams, gets
-        n0 samples and the others n1 with (2/3) g (n1 - n0) = E, g = seconds of the three Grams per sample -- all ranks
-        finish together.  Deterministic in (N, R, P): a model of the B200, not a measurement of the run, so the summation
+        n0 samples and the others n1 with (n1 - n0) (g_s0 + g_rest) = E, g_s0 / g_rest = seconds per sample of the S0 and of the
+        SExp + C_EO Grams -- all ranks finish together (or, when E dominates, the share the solver rank completes inside the
+        others' S0 pass).  Deterministic in (N, R, P): a model of the B200, not a measurement of the run, so the summation
         order of a run is reproducible.  `solverShare` (fraction of an equal share) overrides the model."""
         base, rem = N // R, N % R
         equal = [(r * base + min(r, rem), base + (1 if r < rem else 0)) for r in range(R)]
