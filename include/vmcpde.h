@@ -32,6 +32,10 @@ typedef void* vmcpde_stream;
 
 /* coupling variants: class defaults of net.py:69-71 (the reference selects them by editing source) */
 enum { VMCPDE_NO_ADD = 0, VMCPDE_DIFFERENT_ADD = 1, VMCPDE_JAC_EQ_1 = 2, VMCPDE_ADD_S = 3 };
+/* OR-ed into `variant`: SingleBlock.global_change (net.py:72,80-82,115-116,149-150) -- every block owns global_offset[dim] and
+ * global_scale[1] (flat order: before s1) and maps  result -> scale * result + offset  after the coupling.  The reference's
+ * "inverse" branch (used for sampling) undoes the affine step after the inverse coupling, too; that order is kept as it is. */
+#define VMCPDE_GLOBAL_CHANGE 0x100
 /* latent densities: net.py:197-198 */
 enum { VMCPDE_GAUSS = 0, VMCPDE_STUDENT_T = 1 };
 /* evolution equations: evolutionEq.py:54-60 */
@@ -46,7 +50,7 @@ typedef struct vmcpde_flow_config {
   int32_t depth;            /* number of SingleBlocks */
   int32_t n_hidden_layers;  /* len(intmediate): 1 (streaming fast path, width <= 256) to 3 (generic path, widths <= 32) */
   int32_t hidden;           /* intmediate[0] */
-  int32_t variant;          /* VMCPDE_NO_ADD ... */
+  int32_t variant;          /* VMCPDE_NO_ADD ... , optionally | VMCPDE_GLOBAL_CHANGE */
   int32_t latent;           /* VMCPDE_GAUSS | VMCPDE_STUDENT_T */
   const int32_t* ind_up;    /* host, depth * (dim/2)       : var_state.py:116 */
   const int32_t* ind_down;  /* host, depth * (dim - dim/2) : var_state.py:117 */

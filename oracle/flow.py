@@ -33,6 +33,7 @@ class FlowSpec:
     offset: np.ndarray = None
     inds_up: list = field(default_factory=list)
     inds_down: list = field(default_factory=list)
+    global_change: bool = False   # net.py:72
 
     def __post_init__(self):
         if self.offset is None:
@@ -55,6 +56,9 @@ class FlowSpec:
         out = [("L", (d * (d - 1) // 2,)), ("L_diag", (d,)),
                ("dist_params", (1 if self.latent == "Student_t" else 0,)), ("mu", (d,))]
         for b in sorted(range(self.depth), key=lambda i: f"blocks_{i}"):
+            if self.global_change:   # net.py:80-82; 'global_offset' < 'global_scale' < 's1' in the sorted param dict
+                out.append((f"blocks_{b}/global_offset", (d,)))
+                out.append((f"blocks_{b}/global_scale", (1,)))
             for tn in self.trafo_names():
                 dims = self.trafo_dims(tn, b)
                 for l in range(len(dims) - 1):
@@ -102,6 +106,8 @@ def init_params(spec, seed=1):
             last = name.split("/")[-2] == f"Dense_{nl}"
             scale = 1e-5 if last else 1.0
             theta[a:b] = 2 * scale * (rng.random(b - a) - 0.5)
+        elif name.endswith("global_scale"):
+            theta[a:b] = 1.0     # net.py:81
     return theta
 
 
@@ -117,6 +123,8 @@ def init_params_flax(spec, key):
     theta = np.zeros(P)
     nl = len(spec.hidden)
     for name, (a, b, shape) in sl.items():
+        if name.endswith("global_scale"):
+            theta[a:b] = 1.0     # net.py:81
         if not name.endswith("kernel"):
             continue
         parts = name.split("/")
@@ -198,6 +206,9 @@ def block_forward(x, theta, spec, sl, b):
         v2 = u2 * torch.exp(s1) + s1
     out = torch.zeros_like(x)
     out = out.index_put((torch.tensor(up),), v1).index_put((torch.tensor(down),), v2)
+    if spec.global_change:   # net.py:115-116
+        (a, e, _), (a2, _, _) = sl[f"blocks_{b}/global_offset"], sl[f"blocks_{b}/global_scale"]
+        return theta[a2] * out + theta[a:e], s2.sum() + s1.sum() + torch.log(theta[a2]) * (len(up) + len(down))
     return out, s2.sum() + s1.sum()
 
 
@@ -226,6 +237,9 @@ def block_inverse(x, theta, spec, sl, b):
         u1 = (v1 - s2) * torch.exp(-s2)
     out = torch.zeros_like(x)
     out = out.index_put((torch.tensor(up),), u1).index_put((torch.tensor(down),), u2)
+    if spec.global_change:   # net.py:149-150 (the affine step is undone after the inverse coupling: the reference's order)
+        (a, e, _), (a2, _, _) = sl[f"blocks_{b}/global_offset"], sl[f"blocks_{b}/global_scale"]
+        return (out - theta[a:e]) / theta[a2], -(s1.sum() + s2.sum()) - torch.log(theta[a2]) * (len(up) + len(down))
     return out, -(s1.sum() + s2.sum())
 
 

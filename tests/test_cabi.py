@@ -59,6 +59,14 @@ def test_host_only_entry_points(lib):
     _lib.check(lib.vmcpde_flow_create(ctypes.byref(two), ctypes.byref(h)))       # several hidden layers: net.py:53-58 loops over `intmediate`
     assert lib.vmcpde_flow_num_params(h) == 6 + 4 + 4 + 2 * ((3 + 2 * 3) + (5 + 3 * 5) + (2 + 5 * 2))
     lib.vmcpde_flow_destroy(h)
+    gcf, keep6 = _capi.make_flow_config(4, 2, (5,), "different_add", "Student_t", [[0, 1], [2, 3]], [[2, 3], [0, 1]], np.zeros(4), global_change=True)
+    _lib.check(lib.vmcpde_flow_create(ctypes.byref(gcf), ctypes.byref(h)))       # SingleBlock.global_change: + dim + 1 parameters per block
+    assert lib.vmcpde_flow_num_params(h) == 6 + 4 + 1 + 4 + 2 * (4 * T + 5)
+    _lib.check(lib.vmcpde_flow_param_offsets(h, off))
+    assert list(off) == [0, 6, 10, 11, 15, 15 + 4 * T + 5]
+    lib.vmcpde_flow_destroy(h)
+    badv, keep7 = _capi.make_flow_config(4, 1, (3,), 0x204, "Gauss", [[0, 1]], [[2, 3]], np.zeros(4))
+    assert lib.vmcpde_flow_create(ctypes.byref(badv), ctypes.byref(h)) != 0
     four, keep4 = _capi.make_flow_config(4, 1, (3, 3, 3, 3), "no_add", "Gauss", [[0, 1]], [[2, 3]], np.zeros(4))
     assert lib.vmcpde_flow_create(ctypes.byref(four), ctypes.byref(h)) == 2  # VMCPDE_EUNSUPPORTED: at most three hidden layers
     wide, keep5 = _capi.make_flow_config(4, 1, (3, 40), "no_add", "Gauss", [[0, 1]], [[2, 3]], np.zeros(4))

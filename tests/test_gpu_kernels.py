@@ -42,7 +42,9 @@ CASES = [(2, 4, 1, "no_add", "Gauss", "diffusion", 1000),
          (2, 12, 2, "no_add", "Gauss", "diffusion", 40),
          (6, 0, 1, "no_add", "Gauss", "diffusion", 40),
          (6, 3, (4, 7), "different_add", "Gauss", "advection_hamiltonian_wDiss", 300),   # several hidden layers (net.py:53-58)
-         (4, 2, (3, 5, 2), "no_add", "Student_t", "diffusion", 200)]
+         (4, 2, (3, 5, 2), "no_add", "Student_t", "diffusion", 200),
+         (4, 3, 3, "no_add+gc", "Gauss", "diffusion", 300),                          # global_change (net.py:72,80-82,115-116,149-150)
+         (6, 2, 4, "different_add+gc", "Student_t", "advection_hamiltonian_wDiss", 200)]
 
 
 @pytest.mark.parametrize("d,depth,h,variant,latent,eqname,n", CASES)
@@ -52,10 +54,18 @@ def test_sampler_local_terms_moments_gram(L, d, depth, h, variant, latent, eqnam
     ups, downs, _ = flow.make_index_splits(d, depth, 1)
     off = rng.normal(size=d) * 0.3
     hidden = h if isinstance(h, tuple) else (h,)
-    spec = flow.FlowSpec(dim=d, depth=depth, hidden=hidden, latent=latent, variant=variant, offset=off, inds_up=ups, inds_down=downs)
+    gc = variant.endswith("+gc")
+    variant = variant.replace("+gc", "")
+    spec = flow.FlowSpec(dim=d, depth=depth, hidden=hidden, latent=latent, variant=variant, offset=off, inds_up=ups, inds_down=downs,
+                         global_change=gc)
     th = flow.init_params(spec, 1) + 0.05 * rng.normal(size=spec.num_params)
+    for name, (a_, b_, _) in spec.slices()[0].items():
+        if name.endswith("global_scale"):
+            th[a_:b_] = rng.uniform(0.7, 1.4)
+        if name.endswith("global_offset"):
+            th[a_:b_] = 0.3 * rng.normal(size=b_ - a_)
     st = flow.OracleState(spec, th)
-    cfg, keep = _capi.make_flow_config(d, depth, hidden, variant, latent, ups, downs, off)
+    cfg, keep = _capi.make_flow_config(d, depth, hidden, variant, latent, ups, downs, off, global_change=gc)
     fh = C.c_void_p()
     _lib.check(L.vmcpde_flow_create(C.byref(cfg), C.byref(fh)))
     P = L.vmcpde_flow_num_params(fh)
@@ -104,7 +114,10 @@ def test_sampler_local_terms_moments_gram(L, d, depth, h, variant, latent, eqnam
     y = torch.empty_like(xin); lj = torch.empty_like(E); xb = torch.empty_like(xin); lji = torch.empty_like(E)
     _lib.check(L.vmcpde_flow_transform(fh, _lib.ptr(tht), _lib.ptr(xin), n, 0, _lib.ptr(y), _lib.ptr(lj), None, _lib.stream()))
     _lib.check(L.vmcpde_flow_transform(fh, _lib.ptr(tht), _lib.ptr(y), n, 1, _lib.ptr(xb), _lib.ptr(lji), None, _lib.stream()))
-    assert relerr(xb, xin) < 1e-11 and float((lj + lji).abs().max()) < 1e-10
+    if not gc:
+        assert relerr(xb, xin) < 1e-11 and float((lj + lji).abs().max()) < 1e-10
+    else:   # the reference's inverse branch is not the inverse of its forward branch (net.py:115-116 vs 149-150); the log-Jacobians still cancel
+        assert relerr(xb, xin) > 1e-3
     # ---- first moments, centring, force, three weighted Grams (tdvp.py:36-52, 68-70)
     T = tdvp.OracleTDVP(); T.solve(Eo.numpy(), Oo.numpy(), lpo2.numpy())
     sums = torch.zeros(4 + Pp, device=dev(), dtype=f64)

@@ -23,15 +23,19 @@ def norm_fun(v, S):  # main.py:24-26
 def build(d, depth, h, variant, latent, eqname, offset):
     from vmc_pde_b200 import sampler, var_state, evolutionEq, net
     smp = sampler.Sampler(dim=d, numChains=30, name=latent, mcmc_info={"offset": offset, "bound": 0.25})
+    gc = variant.endswith("+gc")
+    variant = variant.replace("+gc", "")
     net.SingleBlock.different_add = (variant == "different_add")   # the reference selects variants by editing class defaults
+    net.SingleBlock.global_change = gc
     try:
         vs = var_state.VarState(smp, d, 1, depth, network_args={"intmediate": h if isinstance(h, tuple) else (h,), "offset": offset,
                                                                "latentSpaceName": latent, "dim": d})
     finally:
         net.SingleBlock.different_add = False
+        net.SingleBlock.global_change = False
     eq = evolutionEq.EvolutionEquation(dim=d, name=eqname)
     spec = oflow.FlowSpec(dim=d, depth=depth, hidden=h if isinstance(h, tuple) else (h,), latent=latent, variant=variant, offset=offset,
-                          inds_up=vs.net.inds_up, inds_down=vs.net.inds_down)
+                          inds_up=vs.net.inds_up, inds_down=vs.net.inds_down, global_change=gc)
     assert spec.num_params == vs.numParameters
     return smp, vs, eq, spec
 
@@ -42,7 +46,8 @@ RHS_CASES = [(2, 4, 1, "no_add", "Gauss", "diffusion", 10000, np.zeros(2)),     
              (4, 3, 6, "no_add", "Gauss", "diffusion_anisotropic", 3000, np.zeros(4)),
              (2, 4, 2, "no_add", "Gauss", "advection_hamiltonian", 2000, np.ones(2)),              # 'harmonicOsc'
              (2, 4, 85, "no_add", "Gauss", "diffusion", 4096, np.zeros(2)),
-             (4, 3, (6, 4), "no_add", "Gauss", "diffusion", 3000, np.zeros(4))]                 # intmediate of length 2 through the Python surface                       # BASELINE C2 architecture, P = 2053:
+             (4, 3, (6, 4), "no_add", "Gauss", "diffusion", 3000, np.zeros(4)),
+             (4, 3, 4, "no_add+gc", "Gauss", "diffusion", 3000, np.zeros(4))]                   # SingleBlock.global_change through the Python surface                 # intmediate of length 2 through the Python surface                       # BASELINE C2 architecture, P = 2053:
                                                                                                   # blocked eigensolver incl. the lower-triangle mode
 
 

@@ -28,6 +28,9 @@ CASES = [(2, 4, 1, "no_add", "Gauss", "diffusion"),
          (4, 2, 3, "add_s", "Gauss", "diffusion_anisotropic"),
          (4, 2, 3, "jac_eq_1", "Student_t", "advection_hamiltonian"),
          (5, 2, 3, "no_add", "Gauss", "diffusion"),
+         (4, 3, 3, "no_add+gc", "Gauss", "diffusion"),                           # global_change (net.py:72,80-82,115-116,149-150)
+         (6, 2, 4, "different_add+gc", "Student_t", "advection_hamiltonian_wDiss"),
+         (5, 2, (3, 4), "add_s+gc", "Gauss", "diffusion_drift"),
          (8, 12, 4, "no_add", "Student_t", "diffusion"),   # depth > 10: blocks_10 sorts before blocks_2
          (6, 0, 1, "no_add", "Gauss", "diffusion")]
 
@@ -39,15 +42,22 @@ def test_local_terms_and_sampling_match_autograd(hostsim, d, depth, h, variant, 
     ups, downs, _ = flow.make_index_splits(d, depth, 1)
     off = rng.normal(size=d) * 0.3
     hidden = h if isinstance(h, tuple) else (h,)
-    spec = flow.FlowSpec(dim=d, depth=depth, hidden=hidden, latent=latent, variant=variant, offset=off, inds_up=ups, inds_down=downs)
+    gc = variant.endswith("+gc")
+    variant = variant.replace("+gc", "")
+    spec = flow.FlowSpec(dim=d, depth=depth, hidden=hidden, latent=latent, variant=variant, offset=off, inds_up=ups, inds_down=downs,
+                         global_change=gc)
     th = flow.init_params(spec, 1) + 0.05 * rng.normal(size=spec.num_params)
     sl, _ = spec.slices()
     for name, (a, b, shp) in sl.items():
         if name.endswith(f"Dense_{len(hidden)}/kernel"):
             th[a:b] = 0.03 * rng.normal(size=b - a)
+        if name.endswith("global_scale"):
+            th[a:b] = rng.uniform(0.7, 1.4)
+        if name.endswith("global_offset"):
+            th[a:b] = 0.3 * rng.normal(size=b - a)
     st = flow.OracleState(spec, th)
     x = rng.normal(size=(n, d)) * 1.5
-    cfg, keep = _capi.make_flow_config(d, depth, hidden, variant, latent, ups, downs, off)
+    cfg, keep = _capi.make_flow_config(d, depth, hidden, variant, latent, ups, downs, off, global_change=gc)
     assert hostsim.hostsim_num_params(C.byref(cfg)) == spec.num_params
     A = np.ascontiguousarray(tdvp.random_D_factor(d)) if eqname == "diffusion_anisotropic" else None
     eq = _capi.make_equation(eqname, dict(tdvp.EQ_PARAMS.get(eqname, {})), 0.3, A.ctypes.data if A is not None else None)
@@ -72,7 +82,12 @@ def test_local_terms_and_sampling_match_autograd(hostsim, d, depth, h, variant, 
     xo, lpo = torch.func.vmap(lambda zi: flow.sample_single(zi, st.theta, spec, st.sl))(torch.as_tensor(z))
     assert relerr(xs, xo.numpy()) < tol and relerr(lps, lpo.numpy()) < tol
     hostsim.hostsim_logp(C.byref(cfg), P(th), P(xs), C.c_long(n), P(lp2))
-    assert relerr(lp2, lps) < 1e-10
+    if not gc:
+        assert relerr(lp2, lps) < 1e-10
+    else:
+        # the reference's inverse branch (net.py:149-150) is not the inverse of its forward branch (net.py:115-116) unless
+        # scale = 1, offset = 0: the sampled x does not carry the returned log-probability.  Kept as the reference has it.
+        assert relerr(lp2, lps) > 1e-3
 
 
 def test_flow_config_validation(hostsim):

@@ -3,6 +3,7 @@ import ctypes as C
 import numpy as np
 
 VARIANTS = {"no_add": 0, "different_add": 1, "jac_eq_1": 2, "add_s": 3}
+GLOBAL_CHANGE = 0x100   # VMCPDE_GLOBAL_CHANGE, OR-ed into the variant
 LATENTS = {"Gauss": 0, "Student_t": 1}
 EQUATIONS = {"diffusion": 0, "diffusion_drift": 1, "diffusion_anisotropic": 2,
              "advection_hamiltonian": 3, "advection_paper": 4, "advection_hamiltonian_wDiss": 5}
@@ -21,7 +22,7 @@ class Equation(C.Structure):
                 ("t", C.c_double), ("tangents", C.c_void_p)]
 
 
-def make_flow_config(dim, depth, hidden, variant, latent, inds_up, inds_down, offset):
+def make_flow_config(dim, depth, hidden, variant, latent, inds_up, inds_down, offset, global_change=False):
     """Returns (FlowConfig, keepalive) -- keepalive owns the host arrays the struct points to."""
     hidden = tuple(hidden)
     up = np.ascontiguousarray(np.asarray(inds_up, dtype=np.int32).reshape(-1))
@@ -31,7 +32,7 @@ def make_flow_config(dim, depth, hidden, variant, latent, inds_up, inds_down, of
         raise ValueError("offset must have `dim` entries")
     hw = np.ascontiguousarray(np.asarray(hidden if hidden else (0,), dtype=np.int32))
     cfg = FlowConfig(dim, depth, len(hidden), hidden[0] if hidden else 0,
-                     VARIANTS[variant] if isinstance(variant, str) else int(variant),
+                     (VARIANTS[variant] if isinstance(variant, str) else int(variant)) | (GLOBAL_CHANGE if global_change else 0),
                      LATENTS[latent] if isinstance(latent, str) else int(latent),
                      up.ctypes.data_as(C.POINTER(C.c_int32)), down.ctypes.data_as(C.POINTER(C.c_int32)),
                      off.ctypes.data_as(C.POINTER(C.c_double)), hw.ctypes.data_as(C.POINTER(C.c_int32)))

@@ -52,13 +52,13 @@ def round_up(n, m):
 class FlowHandle:
     """Owns a vmcpde_flow (net.INNwProb architecture + index splits + offset)."""
 
-    def __init__(self, dim, depth, hidden, variant, latent, inds_up, inds_down, offset):
+    def __init__(self, dim, depth, hidden, variant, latent, inds_up, inds_down, offset, global_change=False):
         _lib.require_cuda()
         self.L = _lib.load()
         self.dim, self.depth, self.hidden = int(dim), int(depth), tuple(int(h) for h in hidden)
-        self.variant, self.latent = variant, latent
+        self.variant, self.latent, self.global_change = variant, latent, bool(global_change)
         cfg, self._keep = _capi.make_flow_config(self.dim, self.depth, self.hidden, variant, latent, inds_up, inds_down,
-                                                 np.asarray(offset, dtype=np.float64))
+                                                 np.asarray(offset, dtype=np.float64), self.global_change)
         h = C.c_void_p()
         _lib.check(self.L.vmcpde_flow_create(C.byref(cfg), C.byref(h)))
         self.h = h

@@ -78,7 +78,7 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_sample(const vmcpde
   const FlowMeta& m = f->meta;
   cudaStream_t s = (cudaStream_t)stream;
   switch (m.d) {
-#define X(Dv) VMC_CASE(Dv, (m.nl > 1 ? launch_sample<D, 1>(m, theta, key0, key1, first, n, n_total, chi2, x, logp, z_out, s) : launch_sample<D, 0>(m, theta, key0, key1, first, n, n_total, chi2, x, logp, z_out, s)))
+#define X(Dv) VMC_CASE(Dv, ((m.nl > 1 || m.gc) ? launch_sample<D, 1>(m, theta, key0, key1, first, n, n_total, chi2, x, logp, z_out, s) : launch_sample<D, 0>(m, theta, key0, key1, first, n, n_total, chi2, x, logp, z_out, s)))
     VMC_FOR_EACH_DIM(X)
 #undef X
   }
@@ -108,7 +108,7 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_logp(const vmcpde_f
   const FlowMeta& m = f->meta;
   cudaStream_t s = (cudaStream_t)stream;
   switch (m.d) {
-#define X(Dv) VMC_CASE(Dv, (m.nl > 1 ? launch_logp<D, 1>(m, theta, x, n, logp, s) : launch_logp<D, 0>(m, theta, x, n, logp, s)))
+#define X(Dv) VMC_CASE(Dv, ((m.nl > 1 || m.gc) ? launch_logp<D, 1>(m, theta, x, n, logp, s) : launch_logp<D, 0>(m, theta, x, n, logp, s)))
     VMC_FOR_EACH_DIM(X)
 #undef X
   }
@@ -127,7 +127,7 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_local_terms(const v
   EqParams e{eq->mode, eq->D, eq->mu, eq->m, eq->omega, eq->lam, eq->T, eq->gamma, eq->t};
   cudaStream_t s = (cudaStream_t)stream;
   switch (m.d) {
-#define X(Dv) VMC_CASE(Dv, (m.nl > 1 ? launch_local_terms<D, 1>(m, theta, x, n, e, eq->tangents, eloc, logp, grad, lap, O, ldo, s) : launch_local_terms<D, 0>(m, theta, x, n, e, eq->tangents, eloc, logp, grad, lap, O, ldo, s)))
+#define X(Dv) VMC_CASE(Dv, ((m.nl > 1 || m.gc) ? launch_local_terms<D, 1>(m, theta, x, n, e, eq->tangents, eloc, logp, grad, lap, O, ldo, s) : launch_local_terms<D, 0>(m, theta, x, n, e, eq->tangents, eloc, logp, grad, lap, O, ldo, s)))
     VMC_FOR_EACH_DIM(X)
 #undef X
   }
@@ -140,7 +140,7 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_hessian(const vmcpd
   const FlowMeta& m = f->meta;
   cudaStream_t s = (cudaStream_t)stream;
   switch (m.d) {
-#define X(Dv) VMC_CASE(Dv, (m.nl > 1 ? launch_hessian<D, 1>(m, theta, x, n, H, s) : launch_hessian<D, 0>(m, theta, x, n, H, s)))
+#define X(Dv) VMC_CASE(Dv, ((m.nl > 1 || m.gc) ? launch_hessian<D, 1>(m, theta, x, n, H, s) : launch_hessian<D, 0>(m, theta, x, n, H, s)))
     VMC_FOR_EACH_DIM(X)
 #undef X
   }
@@ -154,7 +154,7 @@ extern "C" __attribute__((visibility("default"))) int vmcpde_flow_transform(cons
   const FlowMeta& m = f->meta;
   cudaStream_t s = (cudaStream_t)stream;
   switch (m.d) {
-#define X(Dv) VMC_CASE(Dv, (m.nl > 1 ? launch_transform<D, 1>(m, theta, x, n, inverse, y, logjac, latent_logpdf_of_input, s) : launch_transform<D, 0>(m, theta, x, n, inverse, y, logjac, latent_logpdf_of_input, s)))
+#define X(Dv) VMC_CASE(Dv, ((m.nl > 1 || m.gc) ? launch_transform<D, 1>(m, theta, x, n, inverse, y, logjac, latent_logpdf_of_input, s) : launch_transform<D, 0>(m, theta, x, n, inverse, y, logjac, latent_logpdf_of_input, s)))
     VMC_FOR_EACH_DIM(X)
 #undef X
   }

@@ -47,6 +47,7 @@ constexpr int kMLWidth = 32;     // widest hidden layer of the multi-layer path 
 struct FlowMeta {
   int d, depth, h, variant, latent, P;
   int nl, hw[kMaxLayers];          // hidden layers and their widths (hw[0] == h); nl == 1 is the streaming fast path
+  int gc;                          // SingleBlock.global_change (net.py:72,80-82): per block global_offset[d], global_scale[1]
   int off_L, off_Ldiag, off_dist, off_mu;
   int block_off[kMaxDepth];        // start of "blocks_b" in the flat vector (string-sorted order)
   int8_t up[kMaxDepth][kMaxHalf];   // ind_up   (d/2 entries)
@@ -87,6 +88,10 @@ VMC_HD Trafo trafo_at(const double* th, int off, int din, int dout, const FlowMe
 #endif
   return t;
 }
+
+// Blocks with global_change start with global_offset[d], global_scale[1] ("global_*" sorts before "s1"); the trafos follow.
+VMC_HD bool has_global_change(const FlowMeta& m) { return VMC_ML && m.gc; }
+VMC_HD int block_base(const FlowMeta& m, int b) { return m.block_off[b] + (has_global_change(m) ? m.d + 1 : 0); }
 
 // ---- generic multi-layer path (nl > 1): layer l maps prev (nprev) -> hw[l] with tanh, the last layer -> NO with alpha*tanh.
 // Parameters of layer l: bias[hw[l]], kernel[nprev][hw[l]] (row-major, flax Dense).  `hid` receives the activations of all
@@ -389,7 +394,7 @@ template <int D>
 VMC_HD double block_forward_value(const FlowMeta& m, const double* th, int b, double* z) {
   constexpr int D1 = D / 2, D2 = D - D / 2;
   const int T1 = trafo_size(D1, D2, m), T2 = trafo_size(D2, D1, m);
-  const int o = m.block_off[b];
+  const int o = block_base(m, b);
   double u1[D1], u2[D2], s2[D1], s1[D2], lj = 0.0;
 #pragma unroll
   for (int i = 0; i < D1; ++i) u1[i] = z[m.up[b][i]];
@@ -433,6 +438,13 @@ VMC_HD double block_forward_value(const FlowMeta& m, const double* th, int b, do
   for (int i = 0; i < D1; ++i) z[m.up[b][i]] = u1[i];
 #pragma unroll
   for (int i = 0; i < D2; ++i) z[m.down[b][i]] = u2[i];
+  if (has_global_change(m)) {  // net.py:115-116: scale * result + offset, log-Jacobian + d log(scale)
+    const double* g = th + m.block_off[b];
+    const double sc = g[D];
+#pragma unroll
+    for (int a = 0; a < D; ++a) z[a] = fma(sc, z[a], g[a]);
+    lj += D * log(sc);
+  }
   return lj;
 }
 
@@ -441,7 +453,7 @@ template <int D>
 VMC_HD double block_inverse_value(const FlowMeta& m, const double* th, int b, double* z) {
   constexpr int D1 = D / 2, D2 = D - D / 2;
   const int T1 = trafo_size(D1, D2, m), T2 = trafo_size(D2, D1, m);
-  const int o = m.block_off[b];
+  const int o = block_base(m, b);
   double v1[D1], v2[D2], s1[D2], s2[D1], lj = 0.0;
 #pragma unroll
   for (int i = 0; i < D1; ++i) v1[i] = z[m.up[b][i]];
@@ -485,6 +497,15 @@ VMC_HD double block_inverse_value(const FlowMeta& m, const double* th, int b, do
   for (int i = 0; i < D1; ++i) z[m.up[b][i]] = v1[i];
 #pragma unroll
   for (int i = 0; i < D2; ++i) z[m.down[b][i]] = v2[i];
+  if (has_global_change(m)) {
+    // net.py:149-150, kept as the reference has it: the affine step is undone AFTER the inverse coupling, i.e. this is the
+    // inverse of the forward block only for scale = 1, offset = 0 (the forward block applies it after the coupling, too)
+    const double* g = th + m.block_off[b];
+    const double sc = g[D];
+#pragma unroll
+    for (int a = 0; a < D; ++a) z[a] = (z[a] - g[a]) / sc;
+    lj -= D * log(sc);
+  }
   return lj;
 }
 
@@ -518,7 +539,7 @@ template <int D, int NT>
 VMC_HD void block_forward_jet(const FlowMeta& m, const double* th, int b, const double* w, Jet<NT>* z, Jet<NT>& lj) {
   constexpr int D1 = D / 2, D2 = D - D / 2;
   const int T1 = trafo_size(D1, D2, m), T2 = trafo_size(D2, D1, m);
-  const int o = m.block_off[b];
+  const int o = block_base(m, b);
   Jet<NT> u1[D1], u2[D2];
 #pragma unroll
   for (int i = 0; i < D1; ++i) u1[i] = z[m.up[b][i]];
@@ -566,6 +587,18 @@ VMC_HD void block_forward_jet(const FlowMeta& m, const double* th, int b, const 
   for (int i = 0; i < D1; ++i) z[m.up[b][i]] = u1[i];
 #pragma unroll
   for (int i = 0; i < D2; ++i) z[m.down[b][i]] = u2[i];
+  if (has_global_change(m)) {
+    const double* g = th + m.block_off[b];
+    const double sc = g[D];
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+      z[a].v = fma(sc, z[a].v, g[a]);
+      z[a].l *= sc;
+#pragma unroll
+      for (int k = 0; k < NT; ++k) z[a].g[k] *= sc;
+    }
+    lj.v += D * log(sc);
+  }
 }
 
 // Result of the forward jet pass
@@ -685,7 +718,22 @@ VMC_HD void logp_reverse(const FlowMeta& m, const double* th, const double* zfin
   const int T1 = trafo_size(D1, D2, m), T2 = trafo_size(D2, D1, m);
   double hid[kMaxHidden], dh[kMaxHidden];
   for (int b = m.depth - 1; b >= 0; --b) {
-    const int o = m.block_off[b];
+    const int o = block_base(m, b);
+    if (has_global_change(m)) {
+      // block output = scale * r + offset with r the coupling's output: d/d offset_a = dz_a, d/d scale = sum_a dz_a r_a + d / scale
+      const double* g = th + m.block_off[b];
+      const double sc = g[D];
+      double dsc = D / sc;
+      em.seek(m.block_off[b]);
+#pragma unroll
+      for (int a = 0; a < D; ++a) {
+        em.put(dz[a]);
+        z[a] = (z[a] - g[a]) / sc;
+        dsc = fma(dz[a], z[a], dsc);
+        dz[a] *= sc;
+      }
+      em.put(dsc);
+    }
     const Trafo ts1 = trafo_at(th, o, D1, D2, m), ts2 = trafo_at(th, o + T1, D2, D1, m);
     const Trafo tt1 = trafo_at(th, o + T1 + T2, D1, D2, m), tt2 = trafo_at(th, o + 2 * T1 + T2, D2, D1, m);
     double v1[D1], v2[D2], dv1[D1], dv2[D2];

@@ -31,12 +31,14 @@ inline int make_flow_meta(const vmcpde_flow_config* c, FlowMeta* m, std::string*
     }
     if (sum > kMaxHidden) return fail(VMCPDE_EUNSUPPORTED, "sum of hidden widths must be <= 256");
   }
-  if (c->variant < 0 || c->variant > 3) return fail(VMCPDE_EINVAL, "bad coupling variant");
+  const int variant = c->variant & 0xff, gc = (c->variant & VMCPDE_GLOBAL_CHANGE) ? 1 : 0;
+  if (c->variant < 0 || variant > 3 || (c->variant & ~(0xff | VMCPDE_GLOBAL_CHANGE))) return fail(VMCPDE_EINVAL, "bad coupling variant");
   if (c->latent < 0 || c->latent > 1) return fail(VMCPDE_EINVAL, "bad latent distribution");
   if (c->depth > 0 && c->dim < 2) return fail(VMCPDE_EINVAL, "coupling blocks need dim >= 2");
   const int d = c->dim, d1 = d / 2, d2 = d - d / 2;
   *m = FlowMeta{};
-  m->d = d; m->depth = c->depth; m->h = c->depth > 0 ? widths[0] : 1; m->variant = c->variant; m->latent = c->latent;
+  m->d = d; m->depth = c->depth; m->h = c->depth > 0 ? widths[0] : 1; m->variant = variant; m->latent = c->latent;
+  m->gc = c->depth > 0 ? gc : 0;
   m->nl = c->depth > 0 ? c->n_hidden_layers : 1;
   for (int l = 0; l < kMaxLayers; ++l) m->hw[l] = (c->depth > 0 && l < m->nl) ? widths[l] : (l == 0 ? 1 : 0);
   int off = 0;
@@ -45,7 +47,7 @@ inline int make_flow_meta(const vmcpde_flow_config* c, FlowMeta* m, std::string*
   m->off_dist = off; off += (c->latent == VMCPDE_STUDENT_T) ? 1 : 0;
   m->off_mu = off; off += d;
   const int T1 = trafo_size(d1, d2, *m), T2 = trafo_size(d2, d1, *m);
-  const int per_block = (c->variant == VMCPDE_DIFFERENT_ADD ? 2 : 1) * (T1 + T2);
+  const int per_block = (variant == VMCPDE_DIFFERENT_ADD ? 2 : 1) * (T1 + T2) + (m->gc ? d + 1 : 0);
   std::vector<int> order(c->depth);
   for (int b = 0; b < c->depth; ++b) order[b] = b;
   std::sort(order.begin(), order.end(), [](int a, int b) {

@@ -3,7 +3,7 @@
 The reference builds flax modules and lets JAX trace them; here the classes only DESCRIBE the architecture
 (index splits, widths, coupling variant, latent density) and `apply` dispatches to the sm_100a kernels.
 Parameters are a nested dict with flax's names, {'params': {'L', 'L_diag', 'dist_params', 'mu',
-'myINN': {'blocks_i': {'s1'|'s2'|'t1'|'t2': {'Dense_k': {'bias', 'kernel'}}}}}}, whose leaves are VIEWS into one
+'myINN': {'blocks_i': {['global_offset', 'global_scale',] 's1'|'s2'|'t1'|'t2': {'Dense_k': {'bias', 'kernel'}}}}}}, whose leaves are VIEWS into one
 flat float64 device vector in the reference's flatten order (var_state.py:106-108).
 """
 from dataclasses import dataclass, field
@@ -21,12 +21,10 @@ class SingleBlock:
     jac_eq_1: bool = False
     different_add: bool = False
     no_add: bool = True
-    global_change: bool = False  # not built in this release
+    global_change: bool = False  # net.py:72,80-82: per-block global_scale / global_offset (see INNwProb.global_change)
 
     @classmethod
     def variant_name(cls):
-        if cls.global_change:
-            raise NotImplementedError("SingleBlock.global_change is not built in this release")
         if cls.jac_eq_1:
             return "jac_eq_1"
         if cls.different_add:
@@ -51,6 +49,9 @@ class INNwProb:
     latentSpaceName: str = "Gauss"
     dim: int = 2
     variant: str = None
+    global_change: bool = None     # None: SingleBlock.global_change.  The reference's inverse branch (net.py:149-150) undoes
+                                   # the affine step after the inverse coupling, so with scale != 1 or offset != 0 sampling no
+                                   # longer draws from the evaluated density; kept exactly as the reference has it.
 
     def __post_init__(self):
         self.intmediate = tuple(int(h) for h in self.intmediate)
@@ -60,11 +61,13 @@ class INNwProb:
             raise KeyError(self.latentSpaceName)  # net.py:197-198 has only these two
         if self.variant is None:
             self.variant = SingleBlock.variant_name()
+        if self.global_change is None:
+            self.global_change = bool(SingleBlock.global_change)
         self.depth = len(self.inds_up)
         self.inds_up = [[int(i) for i in np.asarray(u).ravel()] for u in self.inds_up]
         self.inds_down = [[int(i) for i in np.asarray(u).ravel()] for u in self.inds_down]
         self.handle = _kernels.FlowHandle(self.dim, self.depth, self.intmediate, self.variant, self.latentSpaceName,
-                                          self.inds_up, self.inds_down, self.offset)
+                                          self.inds_up, self.inds_down, self.offset, self.global_change)
         self.numParameters = self.handle.P
 
     # ---- flat layout ---------------------------------------------------------------------------
@@ -78,6 +81,9 @@ class INNwProb:
         out = [(("params", "L"), (d * (d - 1) // 2,)), (("params", "L_diag"), (d,)),
                (("params", "dist_params"), (1 if self.latentSpaceName == "Student_t" else 0,)), (("params", "mu"), (d,))]
         for b in sorted(range(self.depth), key=lambda i: f"blocks_{i}"):
+            if self.global_change:      # 'global_offset' < 'global_scale' < 's1'
+                out.append((("params", "myINN", f"blocks_{b}", "global_offset"), (d,)))
+                out.append((("params", "myINN", f"blocks_{b}", "global_scale"), (1,)))
             for tn in self.trafo_names():
                 dims = [d1, *self.intmediate, d2] if tn in ("s1", "t1") else [d2, *self.intmediate, d1]
                 for l in range(len(dims) - 1):
@@ -119,6 +125,8 @@ class INNwProb:
                 scale = 1e-5 if path[-2] == f"Dense_{nl}" else 1.0
                 u = _threefry.uniform01_f32(k, n) * np.float32(0.01)      # initializers.uniform(): scale 1e-2, float32
                 flat[start:start + n] = (np.float32(2.0 * scale) * (u / np.float32(0.01) - np.float32(0.5))).astype(np.float64)
+            elif path[-1] == "global_scale":
+                flat[start] = 1.0                                         # jax.nn.initializers.ones (net.py:81)
             start += n
         flat_t = _kernels.as_dev(flat)
         return self.tree_from_flat(flat_t)
@@ -158,5 +166,6 @@ class INNwProb:
         return (y[0], val[0]) if single else (y, val)
 
 
-# the reference also defines SanityINN (net.py:220-235), a one-parameter rescaling used for debugging only;
-# it is outside the hot path and not built here.
+# the reference also defines SanityINN (net.py:220-235), a one-parameter rescaling with INN's (x, log_jac) interface; its only
+# use is a commented-out line (var_state.py:122) where it could not replace INNwProb (VarState needs a log-probability), so
+# it is not built here.
