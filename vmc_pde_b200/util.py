@@ -1,5 +1,5 @@
-"""util.py of the reference, re-hosted: build_cov_matrix (util.py:21-26), store_infos (:29-32) and Timings (:35-52; the
-reference's own 17 lines, kept as they are because main.py / tdvp.py call them by name)."""
+"""util.py of the reference, re-hosted: build_cov_matrix (util.py:21-26), store_infos (:29-32) and Timings (:35-52; same
+interface, device-synchronised sections)."""
 import time
 import numpy as np
 import torch
@@ -78,23 +78,30 @@ def load_checkpoint(path, vState, stepper=None):
     return float(d["time"]), infos
 
 
-class Timings():
-    """util.py:35-52."""
+class Timings:
+    """Wall-clock sections by name (the interface of util.py:35-52: `timing_dict[name]` is the list of durations in seconds,
+    one per start/stop pair; `print_timings` reports the latest of each and their sum in the reference's format).
+    Kernels are launched asynchronously, so a section is closed only after the device has drained."""
 
     def __init__(self):
         self.timing_dict = {}
+        self._open = {}
+
+    @staticmethod
+    def _now():
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        return time.perf_counter()
 
     def start_timing(self, key):
-        if key not in self.timing_dict.keys():
-            self.timing_dict[key] = []
-        self.timing_dict[key].append(- time.perf_counter())
+        self.timing_dict.setdefault(key, []).append(0.0)
+        self._open[key] = self._now()
 
     def stop_timing(self, key):
-        self.timing_dict[key][-1] += time.perf_counter()
+        self.timing_dict[key][-1] = self._now() - self._open.pop(key)
 
     def print_timings(self):
-        total = 0
-        for key, value in self.timing_dict.items():
-            print(f"\t > {key}: {value[-1]}")
-            total += value[-1]
-        print(f"\t > TOTAL: {total}")
+        latest = {name: runs[-1] for name, runs in self.timing_dict.items()}
+        for name, seconds in latest.items():
+            print(f"\t > {name}: {seconds}")
+        print(f"\t > TOTAL: {sum(latest.values())}")
