@@ -153,6 +153,37 @@ def test_sample_partition_of_the_pipelined_solve():
     assert solver_seconds(8187) == pytest.approx(0.33) and solver_seconds(4096) < solver_seconds(5000) < solver_seconds(8187)
 
 
+def test_sample_partition_invariants_hold_for_any_size():
+    """Property test: whatever (N, ranks, P, solver rank, Gram precision, SExp mode), the shares tile [0, N) in rank order, are
+    a pure function of their arguments, the solver rank's share is 16-aligned (TMA box rows) and never the largest, and the
+    other ranks differ by at most one sample."""
+    from hypothesis import given, settings, strategies as st
+    from vmc_pde_b200.tdvp import TDVP, solve_shard_range
+
+    @settings(max_examples=300, deadline=None)
+    @given(N=st.integers(1, 2 ** 22), R=st.integers(1, 8), P=st.integers(1, 26000), srank=st.integers(0, 7),
+           split=st.booleans(), sexp=st.sampled_from([True, "lazy", False]), share=st.sampled_from([None, 0.0, 0.3, 1.0]))
+    def check(N, R, P, srank, split, sexp, share):
+        T = TDVP(solverRank=srank % R, gramPrecision="split" if split else "fp64", computeSExp=sexp, solverShare=share)
+        part = T.sample_partition(N, R, P)
+        assert part == T.sample_partition(N, R, P) and len(part) == R
+        assert part[0][0] == 0 and all(n >= 0 for _, n in part) and sum(n for _, n in part) == N
+        assert all(part[i][0] + part[i][1] == part[i + 1][0] for i in range(R - 1))
+        Pp = (P + 127) // 128 * 128
+        if T._pipelined(R, P, Pp):
+            n0 = part[T.solverRank][1]
+            others = [n for r, (_, n) in enumerate(part) if r != T.solverRank]
+            assert n0 % 16 == 0 or n0 == N
+            assert max(others) - min(others) <= 1 and (share is not None or n0 <= max(others))
+        else:
+            assert max(n for _, n in part) - min(n for _, n in part) <= 1
+        # eigenvector slices of the sharded solve: 128-aligned, disjoint, complete
+        rows = [solve_shard_range(Pp, R, r) for r in range(R)]
+        assert all(a % 128 == 0 and b % 128 == 0 for a, b in rows) and sum(b for _, b in rows) == Pp
+        assert all(rows[i][0] + rows[i][1] == rows[i + 1][0] for i in range(R - 1))
+    check()
+
+
 def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
