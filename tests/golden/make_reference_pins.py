@@ -21,6 +21,8 @@ not installed).  What each file pins (tests/test_reference_pins.py, tests/test_g
                        architecture 364): first record pins the first sampler draw; the trajectory is free diffusion,
                        covar(t) = covar(0) + 2t, entropy(t) = 4 log(2 pi e (1+2t)) (visualization.py:188);
   ref_diff8_student.npz same with the Student_t latent (host chi^2 is unseeded: bands only).
+  ref_wiener_Tdiff_infos.hdf5  the stored file of ref_wiener_Tdiff itself, byte for byte (written by the reference's
+                       util.store_infos through h5py): the HDF5 reader is tested against it on every machine.
 """
 import os
 import sys
@@ -67,6 +69,9 @@ def main():
             out["ev_index"], out["ev"], out["snr"] = sel, d["ev"][sel], d["snr"][sel]
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
         print(name, n, "records ->", os.path.getsize(os.path.join(HERE, name + ".npz")) // 1024, "KiB")
+    # one stored file as it is (the smallest, 184 KiB): a real h5py / libhdf5 product for the reader test that runs everywhere
+    import shutil
+    shutil.copyfile(os.path.join(REF, FILES["ref_wiener_Tdiff"]), os.path.join(HERE, "ref_wiener_Tdiff_infos.hdf5"))
 
 
 if __name__ == "__main__":

@@ -56,6 +56,23 @@ def test_hdf5_reader_on_the_reference_files_matches_the_fixtures():
         assert d["times"].dtype == np.float64 and d["covar"].shape[1:] == (d["x1"].shape[1],) * 2
 
 
+def test_hdf5_reader_on_a_file_written_by_the_reference(tmp_path):
+    """tests/golden/ref_wiener_Tdiff_infos.hdf5 is one of the reference's stored runs, byte for byte (h5py / libhdf5 output of
+    util.py:29-32): the built-in reader parses it, and what the built-in writer makes of the same data reads back equal."""
+    from vmc_pde_b200 import _hdf5
+    d = _hdf5.read(os.path.join(os.path.dirname(__file__), "golden", "ref_wiener_Tdiff_infos.hdf5"))
+    g = load("ref_wiener_Tdiff")
+    assert sorted(d) == list(g["keys"]) and [str(d[k].shape) for k in sorted(d)] == list(g["shapes"])
+    for k in ("times", "x1", "covar", "integral_1sigma"):
+        assert np.array_equal(d[k][g["index"]], g[k])
+    assert d["times"].dtype == np.float64 and d["times"].shape[0] == d["x1"].shape[0] and d["covar"].shape[1:] == (6, 6)
+    assert np.all(np.diff(d["times"]) > 0)
+    p = str(tmp_path / "again.hdf5")
+    _hdf5.write(p, d)
+    back = _hdf5.read(p)
+    assert sorted(back) == sorted(d) and all(np.array_equal(back[k], d[k]) and back[k].dtype == d[k].dtype for k in d)
+
+
 # ------------------------------------------------------------------------------------------------ RNG + particle integrator
 def test_normal_stream_reproduces_the_t0_record_of_both_stored_particle_runs():
     """exact_dyn.py:108: coords = normal(PRNGKey(0), (N, 6)) + offset."""
