@@ -7,8 +7,9 @@ B-tree and a local heap, contiguous little-endian fixed-point / IEEE datasets):
 
   * `read(path)`  -> {name: ndarray}; understands what h5py 2.x/3.x writes with default settings for such files
     (also chunked layouts without filters are refused loudly rather than misread);
-  * `write(path, {name: array})` writes the same structures (one root group, contiguous datasets), so files written
-    here can be opened by h5py / the reference's plotting scripts.
+  * `write(path, {name: array})` writes the same structures (one root group, contiguous datasets) to the specification, the
+    way libhdf5 laid them out in the reference's own files (which the reader is tested against); meant to be opened by
+    h5py / the reference's plotting scripts, but with no libhdf5 in this image that read-back itself is UNTESTED here.
 
 Pure NumPy; no device code (this is the on-disk side of SURVEY 8f rank 2, not the hot path).
 """

@@ -17,8 +17,9 @@ def build_cov_matrix(L_para, L_diag, dim):
 
 def store_infos(wdir, infos, name="infos.hdf5"):
     """util.py:29-32: one HDF5 dataset per key of `infos` (lists of per-step values) in `wdir + name`.
-    h5py is used when importable; otherwise the built-in writer (_hdf5.py) produces the same flat-group file, readable
-    by h5py and hence by the reference's plotting scripts (visualization.py:141-280, paper_plot/*.py)."""
+    h5py is used when importable; otherwise the built-in writer (_hdf5.py) produces the same flat-group file to the HDF5
+    specification for the reference's plotting scripts (visualization.py:141-280, paper_plot/*.py); a read-back by h5py
+    itself could not be tried in the build image (no libhdf5), the built-in reader handles both."""
     def as_np(v):
         if isinstance(v, torch.Tensor):
             return v.detach().cpu().numpy()
