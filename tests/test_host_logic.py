@@ -248,3 +248,30 @@ def test_bench_reference_arm_runs_on_the_cpu():
     rep = bench.parity_report("C3", {"ev_max": 1.0, "ev_sum": 2.0, "update_S0_update": 3.0, "F_norm": 1.0, "tdvp_error": 0.5,
                                      "entropy": 1.0, "solver_residual": 1e-10})
     assert "values" in rep
+
+
+def test_committed_bench_lines_carry_the_contract_keys():
+    """The bench lines kept under profiles/ (what DESIGN.md quotes) have every key of the bench.py contract, the metric and
+    config of BASELINE.json, and self-consistent numbers (value = 1 / step time; frac = achieved / peak; Gram time < step time)."""
+    import json, pathlib
+    root = pathlib.Path(__file__).resolve().parents[1]
+    base = json.loads((root / "BASELINE.json").read_text())
+    for name, n in (("r02b_bench_n1.json", 1), ("r02_bench_n2.json", 2), ("r02_bench_n4.json", 4), ("r02_bench_n8.json", 8)):
+        txt = (root / "profiles" / name).read_text()
+        d = json.loads(txt[txt.index("{"):])
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                  "dtype", "data", "config", "roofline", "e2e", "clocks", "gpu_launches", "parity"):
+            assert k in d, (name, k)
+        assert d["n_gpus"] == n and d["dtype"] == "f64" and d["higher_is_better"] is True and d["vs_baseline"] is None
+        assert d["unit"] == "steps/s" and "workload" in d["config"] and d["config"]["num_params"] == 8187 and d["config"]["n_samples"] == 2 ** 18
+        assert str(base.get("metric", "")).split()[0].lower() in d["metric"].lower()
+        assert abs(d["value"] * d["ms_per_step"] / 1e3 - 1.0) < 1e-9 and d["warmup"] >= 3
+        r = d["roofline"]
+        assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0.5 < r["frac"] <= 1.05
+        assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(d["e2e"]) and d["e2e"]["h2d_bytes_per_step"] > 0
+        assert d["gpu_launches"] > 0 and d["parity"]["ok"] is True
+        assert 2 * d["stages_ms_per_rhs"]["gram_max_over_ranks"] < d["ms_per_step"]
+        assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        if n == 1:
+            c = d["cpu_baseline"]
+            assert set(("value", "unit", "cores", "kind", "sample")) <= set(c) and c["kind"] == "port" and c["value"] > 0
