@@ -31,6 +31,9 @@ CASES = [(2, 4, 1, "no_add", "Gauss", "diffusion"),
          (4, 3, 3, "no_add+gc", "Gauss", "diffusion"),                           # global_change (net.py:72,80-82,115-116,149-150)
          (6, 2, 4, "different_add+gc", "Student_t", "advection_hamiltonian_wDiss"),
          (5, 2, (3, 4), "add_s+gc", "Gauss", "diffusion_drift"),
+         (8, 2, (3, 4), "jac_eq_1+gc", "Gauss", "diffusion"),
+         (10, 2, (32, 32), "no_add", "Student_t", "diffusion"),                     # the widest layers of the generic path
+         (4, 12, (2, 2), "no_add+gc", "Gauss", "diffusion"),                        # string-sorted block order with per-block extras
          (8, 12, 4, "no_add", "Student_t", "diffusion"),   # depth > 10: blocks_10 sorts before blocks_2
          (6, 0, 1, "no_add", "Gauss", "diffusion")]
 
