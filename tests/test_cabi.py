@@ -41,6 +41,8 @@ def test_host_only_entry_points(lib):
     from vmc_pde_b200 import _capi, _lib
     assert lib.vmcpde_version() == 100
     assert [lib.vmcpde_padded_params(p) for p in (1, 37, 128, 129, 8187, 16385)] == [128, 128, 128, 256, 8192, 16512]
+    # packed upper 128 x 128 tiles of a Pp x Pp Gram matrix (what crosses NVLink): 2080 tiles = 272 MB at Pp = 8192
+    assert [lib.vmcpde_packed_tiles_len(p) for p in (128, 256, 8192)] == [16384, 3 * 16384, 2080 * 16384]
     ups = [[1, 0, 3][:2], [2, 3]]
     cfg, keep = _capi.make_flow_config(4, 2, (5,), "different_add", "Student_t", [[0, 1], [2, 3]], [[2, 3], [0, 1]], np.zeros(4))
     h = ctypes.c_void_p()
